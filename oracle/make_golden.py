@@ -1,0 +1,107 @@
+"""TEST INFRASTRUCTURE -- regenerates ``tests/golden/*`` from the reference itself.
+
+Run in the authoring container (needs ``/root/reference``; the GPU box only sees the committed
+fixtures):
+
+    python oracle/make_golden.py
+
+For a stratified subset of the reference's shipped test pairs it
+  1. rebuilds the model inputs with the reference's own, unmodified preprocessing
+     (``src/utils/protein_utils.py`` via ``oracle/reference_runner.py``),
+  2. runs the reference's unmodified ``Rigid_Body_Docking_Net`` with the shipped checkpoint in fp32
+     (what the reference computes) and in fp64 (the adjudicator, SURVEY 0 / 7 "hard parts"),
+  3. recovers the golden (R*, t*) from the shipped output PDB
+     (``test_sets_pdb/{db5,dips}_equidock_results``) by all-atom Kabsch and records how closely
+     the re-run reproduces the shipped PDB,
+  4. runs one ragged B=3 batch through the reference's *batched* path (dense masked attention,
+     ``rigid_docking_model.py:61-78``) in fp64,
+  5. dumps both shipped checkpoints (weights are data, not source) as flat fp32 ``.npz``.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import reference_runner as rr  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+
+SUBSET = {
+    # smallest ... largest of each test set (N_l+N_r in the comment)
+    'db5': ['1QA9', '1ZHI', '1AVX', '1H1V', '1N2C'],            # 95+102 ... 548+2000
+    'dips': ['kq_1kq1.pdb1_2.dill', 'cf_5cff.pdb2_1.dill',      # 61+61, 87+69
+             'aq_4aqa.pdb1_0.dill', 'hm_4hm1.pdb1_0.dill'],     # 206+237, 446+192
+}
+ARG_KEYS = ['iegmn_n_lays', 'shared_layers', 'skip_weight_h', 'x_connection_init', 'leakyrelu_neg_slope',
+            'num_att_heads', 'iegmn_lay_hid_dim', 'residue_emb_dim', 'input_edge_feats_dim', 'dropout',
+            'nonlin', 'cross_msgs', 'layer_norm', 'layer_norm_coors', 'final_h_layer_norm',
+            'use_dist_in_layers', 'use_edge_features_in_gmn', 'use_mean_node_features', 'graph_nodes',
+            'rot_model', 'noise_decay_rate', 'noise_initial', 'fine_tune', 'graph_max_neighbor',
+            'graph_cutoff']
+OUT_KEYS = ['ligand_coors', 'keypts_ligand', 'keypts_receptor', 'rotation', 'translation']
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    summary = {}
+    for ds, names in SUBSET.items():
+        args, sd = rr.load_checkpoint(ds)
+        ck = {k: v.numpy().astype(np.float32) for k, v in sd.items()}
+        np.savez(os.path.join(OUT, f'{ds}_checkpoint.npz'), **ck)
+        with open(os.path.join(OUT, f'{ds}_args.json'), 'w') as fh:
+            json.dump({k: args[k] for k in ARG_KEYS}, fh, indent=1, sort_keys=True)
+        m32 = rr.build_reference_model(args, sd, torch.float32)
+        m64 = rr.build_reference_model(args, sd, torch.float64)
+        blob, pairs = {}, []
+        summary[ds] = {}
+        for name in names:
+            t0 = time.time()
+            lg, rg = rr.build_pair_graphs(ds, name, args)
+            pair = (rr.graph_to_dict(lg, True), rr.graph_to_dict(rg, False))
+            pairs.append(pair)
+            o32 = rr.run_reference(m32, [pair], torch.float32)
+            o64 = rr.run_reference(m64, [pair], torch.float64)
+            R, t, resid = rr.golden_rigid_from_pdbs(ds, name)
+            lig_file, _, out_file = rr.test_pair_files(ds, name)
+            P, Q = rr.read_all_atoms(lig_file), rr.read_all_atoms(out_file)
+            rerun = (o32['rotation'][0].astype(np.float64) @ P.T).T + o32['translation'][0].astype(np.float64)
+            for side, d in (('lig', pair[0]), ('rec', pair[1])):
+                for k, v in d.items():
+                    blob[f'{name}/{side}/{k}'] = v.numpy()
+            for tag, o, dt in (('ref32', o32, np.float32), ('ref64', o64, np.float64)):
+                for k in OUT_KEYS:
+                    blob[f'{name}/{tag}/{k}'] = o[k][0].astype(dt)
+                for k in ('x_out_ligand', 'x_out_receptor', 'h_out_ligand', 'h_out_receptor'):
+                    blob[f'{name}/{tag}/{k}'] = o[k].astype(dt)
+            blob[f'{name}/pdb/rotation'] = R
+            blob[f'{name}/pdb/translation'] = t
+            summary[ds][name] = {
+                'n_ligand': int(pair[0]['x'].shape[0]), 'n_receptor': int(pair[1]['x'].shape[0]),
+                'e_ligand': int(pair[0]['src'].shape[0]), 'e_receptor': int(pair[1]['src'].shape[0]),
+                'pdb_rigid_fit_residual': resid,
+                'rerun_fp32_vs_shipped_pdb_max_abs': float(np.abs(rerun - Q).max()),
+                'ref_fp32_vs_fp64_coors_max_abs': float(np.abs(o32['ligand_coors'][0] - o64['ligand_coors'][0]).max()),
+            }
+            print(ds, name, summary[ds][name], f'{time.time() - t0:.1f}s', flush=True)
+        # ragged batch through the reference's dense-masked batched path, fp64
+        bsel = [0, 1, 2]
+        ob = rr.run_reference(m64, [pairs[i] for i in bsel], torch.float64)
+        for j, i in enumerate(bsel):
+            for k in OUT_KEYS:
+                blob[f'batched3/{names[i]}/{k}'] = ob[k][j].astype(np.float64)
+        blob['batched3/names'] = np.array([names[i] for i in bsel])
+        blob['names'] = np.array(names)
+        np.savez_compressed(os.path.join(OUT, f'{ds}_pairs.npz'), **blob)
+    with open(os.path.join(OUT, 'summary.json'), 'w') as fh:
+        json.dump(summary, fh, indent=1, sort_keys=True)
+
+
+if __name__ == '__main__':
+    main()
