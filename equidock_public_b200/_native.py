@@ -1,0 +1,96 @@
+"""ctypes binding of ``libeqd_iegmn.so`` (the C ABI declared in ``include/eqd_iegmn.h``).
+
+There is NO fallback: if the CUDA library is missing or a call fails, this raises.  The library is
+built in-tree by ``equidock_public_b200/csrc/build.sh`` (``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libeqd_iegmn.so')
+
+ABI_VERSION = 1
+EDGE_FEATS, N_RBF, HID, H0, H0_PAD, N_RES_TYPES, HEADS, TILE_ROWS = 27, 15, 64, 69, 72, 21, 50, 128
+STATUS_SVD_DEGENERATE, STATUS_NAN, STATUS_DEGREE_OVERFLOW = 1, 2, 4
+
+_vp, _i32, _f32 = C.c_void_p, C.c_int32, C.c_float
+
+
+class EqdGraph(C.Structure):
+    _fields_ = [('n_pairs', _i32), ('n_nodes', _i32), ('n_lig_nodes', _i32), ('n_edges', _i32),
+                ('n_lig_edges', _i32), ('max_in_degree', _i32),
+                ('seg_ptr', _vp), ('row_ptr', _vp), ('col_src', _vp), ('edge_dst', _vp),
+                ('he_lig', _vp), ('he_rec', _vp),
+                ('n_node_tiles', _i32), ('node_tiles', _vp)]
+
+
+class EqdLayerParams(C.Structure):
+    _fields_ = [('dh', _i32), ('dhp', _i32),
+                ('w_proj', _vp), ('b_proj', _vp), ('w_edge1', _vp), ('edge_ln_g', _vp), ('edge_ln_b', _vp),
+                ('w_edge2', _vp), ('b_edge2', _vp), ('w_coor1', _vp), ('b_coor1', _vp), ('w_coor2', _vp),
+                ('b_coor2', _f32),
+                ('w_node1', _vp), ('b_node1', _vp), ('node_ln_g', _vp), ('node_ln_b', _vp),
+                ('w_node2', _vp), ('b_node2', _vp),
+                ('skip_weight_h', _f32), ('x_connection_init', _f32), ('leaky_slope', _f32)]
+
+
+class EqdHeadParams(C.Structure):
+    _fields_ = [('w_mean', _vp), ('b_mean', _vp), ('w_key', _vp), ('w_query', _vp), ('leaky_slope', _f32)]
+
+
+# symbol -> (restype, argtypes); every symbol include/eqd_iegmn.h declares must be listed here
+_G, _L, _H = C.POINTER(EqdGraph), C.POINTER(EqdLayerParams), C.POINTER(EqdHeadParams)
+PROTOTYPES = {
+    'eqd_abi_version': (C.c_int, []),
+    'eqd_workspace_bytes': (C.c_size_t, [_i32, _i32, _i32]),
+    'eqd_embed': (C.c_int, [_G, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'eqd_project': (C.c_int, [_G, _L, _vp, _i32, _vp, _vp]),
+    'eqd_edge_stage': (C.c_int, [_G, _L, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'eqd_node_stage': (C.c_int, [_G, _L, _L, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'eqd_iegmn_layer_forward': (C.c_int, [_G, _L, _L, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'eqd_keypoints': (C.c_int, [_G, _H, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
+    'eqd_kabsch_apply': (C.c_int, [_G, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library once; raises NativeLibraryError if it is absent (no CPU fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise NativeLibraryError(
+            f'{LIB_PATH} not found: build it with equidock_public_b200/csrc/build.sh '
+            '(python -c "import __graft_entry__ as g; g.build()"). This engine has no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    if lib.eqd_abi_version() != ABI_VERSION:
+        raise NativeLibraryError(f'ABI mismatch: library {lib.eqd_abi_version()} vs binding {ABI_VERSION}')
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    if rc <= -1000:
+        raise NativeLibraryError(f'{what}: CUDA error {-(rc + 1000)} at kernel launch')
+    names = {-1: 'EQD_ERR_BAD_ARG', -2: 'EQD_ERR_UNSUPPORTED', -3: 'EQD_ERR_WORKSPACE'}
+    raise NativeLibraryError(f'{what}: {names.get(rc, rc)}')
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor as c_void_p; None -> NULL."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())

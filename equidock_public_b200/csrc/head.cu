@@ -1,0 +1,429 @@
+// Keypoint read-out + Kabsch (IEGMN.forward, rigid_docking_model.py:521-600) and the final rigid
+// transform of the ligand (Rigid_Body_Docking_Net.forward :657-665).  All arithmetic after the
+// mean-pooling GEMM is fp64: the 50-head softmax weights multiply last-layer coordinates that
+// reach O(10^3) A, so this is where fp32 rounding would cost 1e-4 A.
+//
+// Algebra: the reference materialises keys (n x 3200) and compares them with the 3200-d query;
+//   logits[k][j] = <W_K,k h_j , W_Q,k qbar> / sqrt(64) = h_j . u_k,   u_k = W_K,k^T (W_Q,k qbar) / 8
+// so only u (50 x 64) is formed -- 20x fewer FLOPs, same value up to rounding.
+#include "common.cuh"
+
+namespace eqd {
+
+#define HEAD_THREADS 256
+#define HEAD_ULD 65   // padded row stride (doubles) of u[50][64]
+#define HEAD_HLD 65   // padded row stride (floats) of the staged h chunk
+#define HEAD_JC 64    // nodes per staged chunk
+
+// ---- partial column sums of LeakyReLU(W_m h + b_m) over each node tile (:525, :529) -------------
+__global__ void __launch_bounds__(EQD_THREADS, 2)
+head_mean_kernel(eqd_graph g, eqd_head_params hp, const float* __restrict__ h, float* __restrict__ part) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int LD = 68;
+  float* A = smem;                   // [128][68]
+  float* wbuf = smem + EQD_TM * LD;  // weight ring; reused as the reduction scratch [16][64]
+  const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
+  for (int tile = blockIdx.x; tile < g.n_node_tiles; tile += gridDim.x) {
+    const int seg = g.node_tiles[2 * tile], node0 = g.node_tiles[2 * tile + 1];
+    const int nvalid = min(EQD_TM, g.seg_ptr[seg + 1] - node0);
+    tile_load_async(A, LD, h + (long)node0 * EQD_HID, EQD_HID, EQD_TM, nvalid, EQD_HID, tid);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    float acc[8][8], accx[8];
+    acc_set_bias(acc, hp.b_mean, tx);
+    gemm_nn_stream<false>(acc, accx, A + ty * 8 * LD, LD, EQD_HID, hp.w_mean, EQD_HID, EQD_HID, wbuf, tid);
+    float colsum[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) colsum[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (ty * 8 + i < nvalid) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) colsum[j] += lrelu(acc[i][j], hp.leaky_slope);
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wbuf[ty * 64 + col_nn(tx, j)] = colsum[j];
+    __syncthreads();
+    if (tid < 64) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) s += wbuf[q * 64 + tid];
+      part[(long)tile * 64 + tid] = s;
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+struct KeypSmem {
+  double qbar[64];
+  double qk[EQD_HEADS * 64];
+  double u[EQD_HEADS * HEAD_ULD];
+  double state[EQD_HEADS * 5];  // running (max, sum, y.x, y.y, y.z) per head
+  float hc[HEAD_JC * HEAD_HLD];
+  double xc[HEAD_JC * 3];
+};
+
+// One CTA per segment s (a protein): keypoints Y_s[50][3] (:542-560).
+__global__ void __launch_bounds__(HEAD_THREADS)
+keypoints_kernel(eqd_graph g, eqd_head_params hp, const float* __restrict__ h, const double* __restrict__ x,
+                 const float* __restrict__ part, const int* __restrict__ tile_ptr /* [2B+1] first tile of each segment */,
+                 double* __restrict__ keypts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KeypSmem& s = *reinterpret_cast<KeypSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int B = g.n_pairs;
+  const int seg = blockIdx.x;
+  const int pseg = seg < B ? seg + B : seg - B;
+  const int i0 = g.seg_ptr[seg], i1 = g.seg_ptr[seg + 1];
+
+  // query = mean over the PARTNER protein's nodes (:544, :555)
+  if (tid < 64) {
+    double acc = 0.0;
+    for (int t = tile_ptr[pseg]; t < tile_ptr[pseg + 1]; ++t) acc += (double)part[(long)t * 64 + tid];
+    int np = g.seg_ptr[pseg + 1] - g.seg_ptr[pseg];
+    s.qbar[tid] = np > 0 ? acc / (double)np : 0.0;
+  }
+  if (tid < EQD_HEADS) {
+    s.state[tid * 5 + 0] = -INFINITY;
+    s.state[tid * 5 + 1] = 0.0;
+    s.state[tid * 5 + 2] = 0.0;
+    s.state[tid * 5 + 3] = 0.0;
+    s.state[tid * 5 + 4] = 0.0;
+  }
+  __syncthreads();
+  // qk = W_query qbar   (3200 dot products of length 64; one warp per row, coalesced)
+  for (int r = warp; r < EQD_HEADS * 64; r += HEAD_THREADS / 32) {
+    const float* wr = hp.w_query + (long)r * 64;
+    double v = (double)wr[lane] * s.qbar[lane] + (double)wr[lane + 32] * s.qbar[lane + 32];
+    v = warp_sum_d(v);
+    if (lane == 0) s.qk[r] = v;
+  }
+  __syncthreads();
+  // u[k][d] = sum_d' W_key[k*64+d'][d] * qk[k*64+d'] / sqrt(64)
+  for (int o = tid; o < EQD_HEADS * 64; o += HEAD_THREADS) {
+    int k = o >> 6, d = o & 63;
+    const float* wk = hp.w_key + (long)k * 64 * 64 + d;
+    double v = 0.0;
+    for (int dd = 0; dd < 64; ++dd) v += (double)wk[dd * 64] * s.qk[k * 64 + dd];
+    s.u[k * HEAD_ULD + d] = v * 0.125;  // / math.sqrt(d), d = 64 (:545)
+  }
+  __syncthreads();
+
+  // online softmax over this protein's nodes, chunk by chunk; warp w owns heads w, w+8, ...
+  for (int c0 = i0; c0 < i1; c0 += HEAD_JC) {
+    const int nc = min(HEAD_JC, i1 - c0);
+    for (int idx = tid; idx < HEAD_JC * 64; idx += HEAD_THREADS) {
+      int r = idx >> 6, d = idx & 63;
+      s.hc[r * HEAD_HLD + d] = r < nc ? h[(long)(c0 + r) * EQD_HID + d] : 0.f;
+    }
+    for (int idx = tid; idx < HEAD_JC * 3; idx += HEAD_THREADS) s.xc[idx] = idx < nc * 3 ? x[(long)c0 * 3 + idx] : 0.0;
+    __syncthreads();
+    for (int k = warp; k < EQD_HEADS; k += HEAD_THREADS / 32) {
+      const double* uk = s.u + k * HEAD_ULD;
+      double lg[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        int r = lane + 32 * q;
+        const float* hr = s.hc + r * HEAD_HLD;
+        double v = 0.0;
+#pragma unroll 8
+        for (int d = 0; d < 64; ++d) v = fma((double)hr[d], uk[d], v);
+        lg[q] = r < nc ? v : -INFINITY;
+      }
+      double cmax = warp_max_d(fmax(lg[0], lg[1]));
+      double mold = s.state[k * 5 + 0];
+      double mnew = fmax(mold, cmax);
+      double ps = 0.0, px = 0.0, py = 0.0, pz = 0.0;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        int r = lane + 32 * q;
+        double pj = r < nc ? exp(lg[q] - mnew) : 0.0;
+        ps += pj;
+        px += pj * s.xc[r * 3 + 0];
+        py += pj * s.xc[r * 3 + 1];
+        pz += pj * s.xc[r * 3 + 2];
+      }
+      ps = warp_sum_d(ps);
+      px = warp_sum_d(px);
+      py = warp_sum_d(py);
+      pz = warp_sum_d(pz);
+      __syncwarp();
+      if (lane == 0) {
+        double scale = exp(mold - mnew);  // exp(-inf) = 0 on the first chunk
+        s.state[k * 5 + 0] = mnew;
+        s.state[k * 5 + 1] = s.state[k * 5 + 1] * scale + ps;
+        s.state[k * 5 + 2] = s.state[k * 5 + 2] * scale + px;
+        s.state[k * 5 + 3] = s.state[k * 5 + 3] * scale + py;
+        s.state[k * 5 + 4] = s.state[k * 5 + 4] * scale + pz;
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+  if (tid < EQD_HEADS) {
+    double inv = 1.0 / s.state[tid * 5 + 1];
+    double* y = keypts + ((long)seg * EQD_HEADS + tid) * 3;
+    y[0] = s.state[tid * 5 + 2] * inv;
+    y[1] = s.state[tid * 5 + 3] * inv;
+    y[2] = s.state[tid * 5 + 4] * inv;
+  }
+}
+
+// One warp per pair: keypoint means and A = (Y_rec - mean)^T (Y_lig - mean)  (:563-567).
+__global__ void keypoint_cov_kernel(int n_pairs, const double* __restrict__ keypts, double* __restrict__ ymean,
+                                    double* __restrict__ cov) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= n_pairs) return;
+  const double* yl = keypts + (long)b * EQD_HEADS * 3;
+  const double* yr = keypts + (long)(n_pairs + b) * EQD_HEADS * 3;
+  double ml[3], mr[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double a = 0.0, r = 0.0;
+    for (int k = lane; k < EQD_HEADS; k += 32) {
+      a += yl[k * 3 + c];
+      r += yr[k * 3 + c];
+    }
+    ml[c] = warp_sum_d(a) / (double)EQD_HEADS;
+    mr[c] = warp_sum_d(r) / (double)EQD_HEADS;
+  }
+  double A[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) A[q] = 0.0;
+  for (int k = lane; k < EQD_HEADS; k += 32) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) A[r * 3 + c] += (yr[k * 3 + r] - mr[r]) * (yl[k * 3 + c] - ml[c]);
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) A[q] = warp_sum_d(A[q]);
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      ymean[(long)b * 3 + c] = ml[c];
+      ymean[(long)(n_pairs + b) * 3 + c] = mr[c];
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) cov[(long)b * 9 + q] = A[q];
+  }
+}
+
+// 3x3 SVD A = U diag(S) V^T by one-sided (Hestenes) Jacobi in fp64, singular values sorted
+// descending.  Columns of U belonging to a zero singular value are completed to an orthonormal
+// basis (such inputs are flagged by the guard anyway).
+__device__ void svd3(const double (&A)[9], double (&U)[9], double (&S)[3], double (&V)[9]) {
+  double G[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) G[q] = A[q];
+  V[0] = 1; V[1] = 0; V[2] = 0; V[3] = 0; V[4] = 1; V[5] = 0; V[6] = 0; V[7] = 0; V[8] = 1;
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    double off = 0.0;
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+      double alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        alpha += G[r * 3 + p] * G[r * 3 + p];
+        beta += G[r * 3 + q] * G[r * 3 + q];
+        gamma += G[r * 3 + p] * G[r * 3 + q];
+      }
+      if (gamma == 0.0) continue;
+      double lim = sqrt(alpha * beta);
+      if (fabs(gamma) <= 1e-18 * lim) continue;
+      off = fmax(off, fabs(gamma) / fmax(lim, 1e-300));
+      double zeta = (beta - alpha) / (2.0 * gamma);
+      double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+      double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        double gp = G[r * 3 + p], gq = G[r * 3 + q];
+        G[r * 3 + p] = c * gp - sn * gq;
+        G[r * 3 + q] = sn * gp + c * gq;
+        double vp = V[r * 3 + p], vq = V[r * 3 + q];
+        V[r * 3 + p] = c * vp - sn * vq;
+        V[r * 3 + q] = sn * vp + c * vq;
+      }
+    }
+    if (off < 1e-15) break;
+  }
+  double nrm[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) nrm[c] = sqrt(G[c] * G[c] + G[3 + c] * G[3 + c] + G[6 + c] * G[6 + c]);
+  // sort columns by descending singular value (3-element network)
+  int idx[3] = {0, 1, 2};
+#define EQD_CSWAP(a, b) if (nrm[idx[a]] < nrm[idx[b]]) { int t_ = idx[a]; idx[a] = idx[b]; idx[b] = t_; }
+  EQD_CSWAP(0, 1) EQD_CSWAP(1, 2) EQD_CSWAP(0, 1)
+#undef EQD_CSWAP
+  double Vs[9];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    int sc = idx[c];
+    S[c] = nrm[sc];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      Vs[r * 3 + c] = V[r * 3 + sc];
+      U[r * 3 + c] = nrm[sc] > 0.0 ? G[r * 3 + sc] / nrm[sc] : 0.0;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) V[q] = Vs[q];
+  // complete U if rank deficient: u2 = u0 x u1 (only matters for flagged inputs)
+  if (S[2] <= 1e-300 * S[0] || S[2] == 0.0) {
+    U[2] = U[3] * U[7] - U[6] * U[4];
+    U[5] = U[6] * U[1] - U[0] * U[7];
+    U[8] = U[0] * U[4] - U[3] * U[1];
+  }
+}
+
+// One CTA per pair: thread 0 solves Kabsch (:571-589), then all threads move that pair's ligand (:665).
+__global__ void kabsch_apply_kernel(eqd_graph g, const double* __restrict__ cov, const double* __restrict__ ymean,
+                                    const float* __restrict__ x_lig_in, const int* __restrict__ pair_mask,
+                                    float* __restrict__ rot, float* __restrict__ trans, float* __restrict__ ligand_out,
+                                    double* __restrict__ sing, int* __restrict__ status) {
+  const int b = blockIdx.x;
+  if (pair_mask && pair_mask[b] == 0) return;
+  __shared__ double Tb[12];
+  if (threadIdx.x == 0) {
+    double A[9], U[9], S[3], V[9];
+    bool nan = false;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+      A[q] = cov[(long)b * 9 + q];
+      nan |= !(A[q] == A[q]);
+    }
+    svd3(A, U, S, V);
+    int st = 0;
+    if (nan) st |= EQD_STATUS_NAN;
+    // guard of :574, evaluated on the fp32-rounded singular values like the reference's fp32 S
+    {
+      float s0 = (float)S[0], s1 = (float)S[1], s2 = (float)S[2];
+      float q0 = s0 * s0, q1 = s1 * s1, q2 = s2 * s2;
+      float gap = fminf(fminf(fabsf(q0 - q1), fabsf(q0 - q2)), fabsf(q1 - q2));
+      if (fminf(fminf(s0, s1), s2) < 1e-3f || gap < 1e-2f) st |= EQD_STATUS_SVD_DEGENERATE;
+    }
+    double det = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) +
+                 A[2] * (A[3] * A[7] - A[4] * A[6]);
+    double sg = det > 0.0 ? 1.0 : (det < 0.0 ? -1.0 : 0.0);  // torch.sign(torch.det(A)) :586
+    const double* ml = ymean + (long)b * 3;
+    const double* mr = ymean + (long)(g.n_pairs + b) * 3;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)  // T = U diag(1,1,sg) V^T :587
+        Tb[r * 3 + c] = U[r * 3 + 0] * V[c * 3 + 0] + U[r * 3 + 1] * V[c * 3 + 1] + sg * U[r * 3 + 2] * V[c * 3 + 2];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)  // b = mean_rec - T mean_lig :589
+      Tb[9 + r] = mr[r] - (Tb[r * 3 + 0] * ml[0] + Tb[r * 3 + 1] * ml[1] + Tb[r * 3 + 2] * ml[2]);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) rot[(long)b * 9 + q] = (float)Tb[q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      trans[(long)b * 3 + q] = (float)Tb[9 + q];
+      sing[(long)b * 3 + q] = S[q];
+    }
+    status[b] = st;
+  }
+  __syncthreads();
+  const int i0 = g.seg_ptr[b], i1 = g.seg_ptr[b + 1];
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    double px = (double)x_lig_in[(long)i * 3 + 0], py = (double)x_lig_in[(long)i * 3 + 1],
+           pz = (double)x_lig_in[(long)i * 3 + 2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      ligand_out[(long)i * 3 + r] = (float)(Tb[r * 3 + 0] * px + Tb[r * 3 + 1] * py + Tb[r * 3 + 2] * pz + Tb[9 + r]);
+  }
+}
+
+// tile_ptr[s] = index of the first node tile of segment s (tiles are emitted segment by segment)
+__global__ void tile_ptr_kernel(eqd_graph g, int* __restrict__ tile_ptr) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  int nseg = 2 * g.n_pairs;
+  if (s > nseg) return;
+  if (s == nseg) {
+    tile_ptr[s] = g.n_node_tiles;
+    return;
+  }
+  // binary search for the first tile whose segment >= s
+  int lo = 0, hi = g.n_node_tiles;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (g.node_tiles[2 * mid] < s) lo = mid + 1; else hi = mid;
+  }
+  tile_ptr[s] = lo;
+}
+
+}  // namespace eqd
+
+static inline size_t eqd_align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" int eqd_abi_version(void) { return EQD_ABI_VERSION; }
+
+extern "C" size_t eqd_workspace_bytes(int32_t n_nodes, int32_t n_node_tiles, int32_t n_pairs) {
+  (void)n_nodes;
+  return eqd_align256((size_t)(n_node_tiles > 0 ? n_node_tiles : 1) * 64 * sizeof(float)) +
+         eqd_align256((size_t)(2 * (n_pairs > 0 ? n_pairs : 0) + 1) * sizeof(int));
+}
+
+extern "C" int eqd_keypoints(const eqd_graph* g, const eqd_head_params* hp, const float* h, const double* x,
+                             void* workspace, size_t workspace_bytes, double* keypts, double* ymean, double* cov,
+                             void* stream) {
+  if (!g || !hp || !h || !x || !workspace || !keypts || !ymean || !cov) return EQD_ERR_BAD_ARG;
+  if (workspace_bytes < eqd_workspace_bytes(g->n_nodes, g->n_node_tiles, g->n_pairs)) return EQD_ERR_WORKSPACE;
+  if (g->n_pairs <= 0) return EQD_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = reinterpret_cast<float*>(workspace);
+  int* tile_ptr = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(workspace) +
+                                         eqd_align256((size_t)(g->n_node_tiles > 0 ? g->n_node_tiles : 1) * 64 * sizeof(float)));
+  {
+    size_t smem = (size_t)(EQD_TM * 68 + 2 * EQD_WCHUNK * EQD_WLD) * sizeof(float);
+    cudaFuncSetAttribute(eqd::head_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int grid = g->n_node_tiles < 148 * 2 ? g->n_node_tiles : 148 * 2;
+    eqd::head_mean_kernel<<<grid, EQD_THREADS, smem, st>>>(*g, *hp, h, part);
+    EQD_CUDA_LAUNCH_CHECK();
+  }
+  {
+    int nseg1 = 2 * g->n_pairs + 1;
+    eqd::tile_ptr_kernel<<<(nseg1 + 127) / 128, 128, 0, st>>>(*g, tile_ptr);
+    EQD_CUDA_LAUNCH_CHECK();
+  }
+  {
+    size_t smem = sizeof(eqd::KeypSmem);
+    cudaFuncSetAttribute(eqd::keypoints_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    eqd::keypoints_kernel<<<2 * g->n_pairs, HEAD_THREADS, smem, st>>>(*g, *hp, h, x, part, tile_ptr, keypts);
+    EQD_CUDA_LAUNCH_CHECK();
+  }
+  {
+    int warps_per_block = 4;
+    int grid = (g->n_pairs + warps_per_block - 1) / warps_per_block;
+    eqd::keypoint_cov_kernel<<<grid, warps_per_block * 32, 0, st>>>(g->n_pairs, keypts, ymean, cov);
+    EQD_CUDA_LAUNCH_CHECK();
+  }
+  return EQD_OK;
+}
+
+extern "C" int eqd_kabsch_apply(const eqd_graph* g, const double* cov, const double* ymean, const float* x_lig_in,
+                                const int32_t* pair_mask, float* rot, float* trans, float* ligand_out, double* sing,
+                                int32_t* status, void* stream) {
+  if (!g || !cov || !ymean || !x_lig_in || !rot || !trans || !ligand_out || !sing || !status) return EQD_ERR_BAD_ARG;
+  if (g->n_pairs <= 0) return EQD_OK;
+  eqd::kabsch_apply_kernel<<<g->n_pairs, 128, 0, (cudaStream_t)stream>>>(*g, cov, ymean, x_lig_in, pair_mask, rot,
+                                                                        trans, ligand_out, sing, status);
+  EQD_CUDA_LAUNCH_CHECK();
+  return EQD_OK;
+}

@@ -1,0 +1,265 @@
+"""Host side of the B200 IEGMN forward engine: weight repacking, batch topology ("plan"), buffer
+management and kernel sequencing over the C ABI (``include/eqd_iegmn.h``).
+
+PyTorch is used for device memory, streams and a few index-building ops only; all arithmetic of
+the hot path runs in the hand-written sm_100a kernels of ``csrc/``.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .hetero_graph import LIGAND, LL, RECEPTOR, RR
+
+
+def _dev_f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class PackedLayer:
+    """One IEGMN_Layer's parameters repacked k-major for the kernels (see eqd_layer_params)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], device, skip_weight_h: float, x_connection_init: float,
+                 leaky_slope: float):
+        f = lambda k: _dev_f32(sd[k], device)
+        w1, b1 = f('edge_mlp.0.weight'), f('edge_mlp.0.bias')
+        wq, wk, wv = f('att_mlp_Q.0.weight'), f('att_mlp_K.0.weight'), f('att_mlp_V.0.weight')
+        w5, b5 = f('node_mlp.0.weight'), f('node_mlp.0.bias')
+        w6, b6 = f('node_mlp.4.weight'), f('node_mlp.4.bias')
+        dh = int(wq.shape[0])
+        if dh not in (nat.HID, nat.H0):
+            raise ValueError(f'IEGMN layer width {dh} is not supported by the CUDA engine (64 or 69)')
+        dhp = nat.HID if dh == nat.HID else nat.H0_PAD
+        n_e = nat.EDGE_FEATS + nat.N_RBF
+        assert w1.shape == (nat.HID, 2 * dh + n_e) and w5.shape == (dh, 2 * dh + nat.HID + nat.H0)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
+        pw = 128 + 3 * dhp
+        w_proj, b_proj = z(dhp, pw), z(pw)
+        w_proj[:dh, 0:64] = w1[:, 0:dh].t()
+        w_proj[:dh, 64:128] = w1[:, dh:2 * dh].t()
+        w_proj[:dh, 128:128 + dh] = wq.t()
+        w_proj[:dh, 128 + dhp:128 + dhp + dh] = wk.t()
+        w_proj[:dh, 128 + 2 * dhp:128 + 2 * dhp + dh] = wv.t()
+        b_proj[64:128] = b1
+        w_edge1 = z(44, 64)
+        w_edge1[:n_e] = w1[:, 2 * dh:].t()
+        w_node1 = z(2 * dhp + 64 + nat.H0_PAD, dhp)
+        w_node1[0:dh, :dh] = w5[:, 0:dh].t()
+        w_node1[dhp:dhp + 64, :dh] = w5[:, dh:dh + 64].t()
+        w_node1[dhp + 64:dhp + 64 + dh, :dh] = w5[:, dh + 64:2 * dh + 64].t()
+        w_node1[2 * dhp + 64:2 * dhp + 64 + nat.H0, :dh] = w5[:, 2 * dh + 64:].t()
+        pad = lambda v: torch.cat([v, z(dhp - dh)]) if dhp > dh else v.clone()
+        w_node2 = z(dhp, 64)
+        w_node2[:dh] = w6.t()
+        self.dh, self.dhp = dh, dhp
+        self.t = {
+            'w_proj': w_proj, 'b_proj': b_proj, 'w_edge1': w_edge1,
+            'edge_ln_g': f('edge_mlp.3.weight'), 'edge_ln_b': f('edge_mlp.3.bias'),
+            'w_edge2': f('edge_mlp.4.weight').t().contiguous(), 'b_edge2': f('edge_mlp.4.bias'),
+            'w_coor1': f('coors_mlp.0.weight').t().contiguous(), 'b_coor1': f('coors_mlp.0.bias'),
+            'w_coor2': f('coors_mlp.4.weight').reshape(-1).contiguous(),
+            'w_node1': w_node1, 'b_node1': pad(b5),
+            'node_ln_g': pad(f('node_mlp.3.weight')), 'node_ln_b': pad(f('node_mlp.3.bias')),
+            'w_node2': w_node2, 'b_node2': b6,
+        }
+        s = nat.EqdLayerParams()
+        s.dh, s.dhp = dh, dhp
+        for k, v in self.t.items():
+            setattr(s, k, v.data_ptr())
+        s.b_coor2 = float(sd['coors_mlp.4.bias'].detach().reshape(-1)[0].item())
+        s.skip_weight_h, s.x_connection_init, s.leaky_slope = skip_weight_h, x_connection_init, leaky_slope
+        self.struct = s
+
+
+class PackedHead:
+    def __init__(self, w_mean, b_mean, w_key, w_query, device, leaky_slope: float):
+        self.t = {'w_mean': _dev_f32(w_mean, device).t().contiguous(), 'b_mean': _dev_f32(b_mean, device),
+                  'w_key': _dev_f32(w_key, device), 'w_query': _dev_f32(w_query, device)}
+        assert self.t['w_key'].shape == (nat.HEADS * nat.HID, nat.HID)
+        s = nat.EqdHeadParams()
+        for k, v in self.t.items():
+            setattr(s, k, v.data_ptr())
+        s.leaky_slope = leaky_slope
+        self.struct = s
+
+
+class GraphPlan:
+    """Batch topology in the engine's layout (see the numbering comment in eqd_iegmn.h)."""
+
+    def __init__(self, n_lig: Sequence[int], n_rec: Sequence[int], src_l, dst_l, src_r, dst_r, he_l, he_r,
+                 device, max_in_degree: int = 10):
+        n_lig = [int(v) for v in n_lig]
+        n_rec = [int(v) for v in n_rec]
+        assert len(n_lig) == len(n_rec) and len(n_lig) > 0
+        self.n_pairs = len(n_lig)
+        self.n_lig_list, self.n_rec_list = n_lig, n_rec
+        self.N_l, self.N_r = sum(n_lig), sum(n_rec)
+        self.N = self.N_l + self.N_r
+        self.device = device
+        i32 = dict(dtype=torch.int32, device=device)
+        src_l, dst_l = src_l.to(**i32), dst_l.to(**i32)
+        src_r, dst_r = src_r.to(**i32), dst_r.to(**i32)
+        self.E_l, self.E_r = int(src_l.shape[0]), int(src_r.shape[0])
+        self.E = self.E_l + self.E_r
+        self.col_src = torch.cat([src_l, src_r + self.N_l]).contiguous()
+        self.edge_dst = torch.cat([dst_l, dst_r + self.N_l]).contiguous()
+        # CSR by destination; the kernels assume edges arrive grouped by ascending destination
+        # (protein_utils.py:339-346 emits them that way).  `unsorted` stays on the device and is
+        # read together with the per-pair status (one sync per forward).
+        d64 = self.edge_dst.long()
+        self.unsorted = ((d64[1:] < d64[:-1]).any() if self.E > 1 else torch.zeros((), dtype=torch.bool, device=device))
+        deg = torch.bincount(d64, minlength=self.N)
+        self.row_ptr = torch.zeros(self.N + 1, **i32)
+        self.row_ptr[1:] = torch.cumsum(deg, 0).to(torch.int32)
+        self.he_l = he_l.to(device=device, dtype=torch.float32).contiguous()
+        self.he_r = he_r.to(device=device, dtype=torch.float32).contiguous()
+        assert self.he_l.shape == (self.E_l, nat.EDGE_FEATS) and self.he_r.shape == (self.E_r, nat.EDGE_FEATS)
+        seg = np.zeros(2 * self.n_pairs + 1, dtype=np.int64)
+        seg[1:] = np.cumsum(np.asarray(n_lig + n_rec, dtype=np.int64))
+        tiles = []
+        for s in range(2 * self.n_pairs):
+            for n0 in range(int(seg[s]), int(seg[s + 1]), nat.TILE_ROWS):
+                tiles.append((s, n0))
+        self.seg_ptr_host = seg
+        self.n_node_tiles = len(tiles)
+        small = torch.from_numpy(np.concatenate([seg.astype(np.int32),
+                                                 np.asarray(tiles, dtype=np.int32).reshape(-1)]))
+        small = small.to(device, non_blocking=True)
+        self.seg_ptr = small[:2 * self.n_pairs + 1]
+        self.node_tiles = small[2 * self.n_pairs + 1:]
+        self._small = small
+        g = nat.EqdGraph()
+        g.n_pairs, g.n_nodes, g.n_lig_nodes = self.n_pairs, self.N, self.N_l
+        g.n_edges, g.n_lig_edges, g.max_in_degree = self.E, self.E_l, int(max_in_degree)
+        g.seg_ptr, g.row_ptr = self.seg_ptr.data_ptr(), self.row_ptr.data_ptr()
+        g.col_src, g.edge_dst = self.col_src.data_ptr(), self.edge_dst.data_ptr()
+        g.he_lig, g.he_rec = self.he_l.data_ptr(), self.he_r.data_ptr()
+        g.n_node_tiles, g.node_tiles = self.n_node_tiles, self.node_tiles.data_ptr()
+        self.struct = g
+
+    @classmethod
+    def from_graph(cls, graph, device, max_in_degree: int = 10) -> 'GraphPlan':
+        """From a batched DGL heterograph (train_utils.py:61-100) or a ``PairGraphBatch``."""
+        n_l = graph.batch_num_nodes(LIGAND).tolist()
+        n_r = graph.batch_num_nodes(RECEPTOR).tolist()
+        src_l, dst_l = graph.edges(etype=LL)
+        src_r, dst_r = graph.edges(etype=RR)
+        return cls(n_l, n_r, src_l, dst_l, src_r, dst_r, graph.edges[LL].data['he'], graph.edges[RR].data['he'],
+                   device, max_in_degree)
+
+
+def _sorted_copy(plan_args):
+    """Slow path for graphs whose edges are not grouped by destination: stable sort + permute."""
+    n_l, n_r, src_l, dst_l, src_r, dst_r, he_l, he_r, device, mid = plan_args
+    out = []
+    for s, d, he in ((src_l, dst_l, he_l), (src_r, dst_r, he_r)):
+        perm = torch.sort(d.long(), stable=True).indices
+        out.append((s[perm], d[perm], he[perm]))
+    (sl, dl, hl), (sr, dr, hr) = out
+    return n_l, n_r, sl, dl, sr, dr, hl, hr, device, mid
+
+
+class IEGMNEngine:
+    """Runs the IEGMN stack + keypoints + Kabsch for one plan on the current CUDA stream."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise nat.NativeLibraryError('the IEGMN engine runs on a CUDA device only (no CPU fallback)')
+        self.lib = nat.load()
+
+    def forward(self, plan: GraphPlan, emb: torch.Tensor, layers: List[PackedLayer], head: PackedHead,
+                res_l, res_r, mu_l, mu_r, x_l, x_r, check_status: bool = True, log=None) -> Dict[str, torch.Tensor]:
+        lib, dev = self.lib, self.device
+        g = C.byref(plan.struct)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        N, B = plan.N, plan.n_pairs
+        f32 = dict(dtype=torch.float32, device=dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        cf = lambda t: t.to(**f32).contiguous()
+        res_l, res_r, mu_l, mu_r, x_l, x_r = map(cf, (res_l, res_r, mu_l, mu_r, x_l, x_r))
+        assert x_l.shape == (plan.N_l, 3) and x_r.shape == (plan.N_r, 3)
+        h0 = torch.empty(N, nat.H0_PAD, **f32)
+        x0 = torch.empty(N, 3, **f64)
+        xa, xb = torch.empty(N, 3, **f64), torch.empty(N, 3, **f64)
+        ha, hb = torch.empty(N, nat.HID, **f32), torch.empty(N, nat.HID, **f32)
+        pa, pb = torch.empty(N, 128 + 3 * nat.H0_PAD, **f32), torch.empty(N, 128 + 3 * nat.H0_PAD, **f32)
+        aggr = torch.empty(N, nat.HID, **f32)
+        status = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+        nat.check(lib.eqd_embed(g, nat.ptr(emb), nat.ptr(res_l), nat.ptr(res_r), nat.ptr(mu_l), nat.ptr(mu_r),
+                                nat.ptr(x_l), nat.ptr(x_r), nat.ptr(h0), nat.ptr(x0), st), 'eqd_embed')
+        nat.check(lib.eqd_project(g, C.byref(layers[0].struct), nat.ptr(h0), nat.H0_PAD, nat.ptr(pa), st),
+                  'eqd_project')
+        h_in, ldh, x_in = h0, nat.H0_PAD, x0
+        h_out, x_out = ha, xa
+        for li, lay in enumerate(layers):
+            nxt = layers[li + 1] if li + 1 < len(layers) else None
+            nat.check(lib.eqd_iegmn_layer_forward(
+                g, C.byref(lay.struct), C.byref(nxt.struct) if nxt is not None else None,
+                nat.ptr(h_in), ldh, nat.ptr(h0), nat.ptr(x_in), nat.ptr(x0), nat.ptr(pa), nat.ptr(pb),
+                nat.ptr(aggr), nat.ptr(h_out), nat.ptr(x_out), nat.ptr(status), st), f'eqd_iegmn_layer_forward[{li}]')
+            pa, pb = pb, pa
+            h_in, ldh, x_in = h_out, nat.HID, x_out
+            h_out = hb if h_out is ha else ha
+            x_out = xb if x_out is xa else xa
+        h_fin, x_fin = h_in, x_in
+        ws_bytes = lib.eqd_workspace_bytes(N, plan.n_node_tiles, B)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        keyp = torch.empty(2 * B, nat.HEADS, 3, **f64)
+        ymean = torch.empty(2 * B, 3, **f64)
+        cov = torch.empty(B, 9, **f64)
+        nat.check(lib.eqd_keypoints(g, C.byref(head.struct), nat.ptr(h_fin), nat.ptr(x_fin), nat.ptr(ws), ws_bytes,
+                                    nat.ptr(keyp), nat.ptr(ymean), nat.ptr(cov), st), 'eqd_keypoints')
+        rot, trans = torch.empty(B, 3, 3, **f32), torch.empty(B, 1, 3, **f32)
+        lig_out = torch.empty(plan.N_l, 3, **f32)
+        sing = torch.empty(B, 3, **f64)
+        kab = lambda mask: nat.check(lib.eqd_kabsch_apply(
+            g, nat.ptr(cov), nat.ptr(ymean), nat.ptr(x_l), nat.ptr(mask), nat.ptr(rot), nat.ptr(trans),
+            nat.ptr(lig_out), nat.ptr(sing), nat.ptr(status), st), 'eqd_kabsch_apply')
+        kab(None)
+        out = {'ligand_coors': lig_out, 'keypts': keyp, 'rotation': rot, 'translation': trans, 'h': h_fin,
+               'x64': x_fin, 'cov': cov, 'sing': sing, 'status': status, 'unsorted': plan.unsorted}
+        if check_status:
+            self.resolve_status(plan, out, kab, log)
+        return out
+
+    def resolve_status(self, plan: GraphPlan, out, kab, log=None):
+        """The ONE host sync of a forward: reads the status words and replays the reference's
+        host-side control flow for flagged pairs (rigid_docking_model.py:570-584)."""
+        st_host = torch.cat([out['status'], out['unsorted'].to(torch.int32).reshape(1)]).cpu()
+        if int(st_host[-1]) != 0:
+            raise UnsortedEdges()
+        if int(st_host[plan.n_pairs]) & nat.STATUS_DEGREE_OVERFLOW:
+            raise nat.NativeLibraryError(
+                f'a node has more than max_in_degree={plan.struct.max_in_degree} in-edges; '
+                'pass the true bound (args["graph_max_neighbor"])')
+        pair_st = st_host[:plan.n_pairs]
+        if not bool(pair_st.any()):
+            return
+        if bool((pair_st & nat.STATUS_NAN).any()):
+            raise AssertionError('NaN in the Kabsch covariance (rigid_docking_model.py:570)')
+        eye_idx = torch.tensor([0, 4, 8], device=self.device)
+        for b in torch.nonzero(pair_st & nat.STATUS_SVD_DEGENERATE).reshape(-1).tolist():
+            mask = torch.zeros(plan.n_pairs, dtype=torch.int32, device=self.device)
+            mask[b] = 1
+            num_it = 0
+            while True:
+                noise = torch.rand(3, 3)  # same CPU-generator draw as the reference (:578)
+                out['cov'][b, eye_idx] += torch.diagonal(noise).to(self.device, torch.float64)
+                kab(mask)
+                num_it += 1
+                if num_it > 10:  # the reference gives up before re-testing the 11th attempt (:582-584)
+                    if log is not None:
+                        log('SVD consistently numerically unstable! Exitting ... ')
+                    sys.exit(1)
+                if int(out['status'][b].item()) & nat.STATUS_SVD_DEGENERATE == 0:
+                    break
+
+
+class UnsortedEdges(RuntimeError):
+    pass

@@ -1,0 +1,179 @@
+/*
+ * eqd_iegmn.h -- C ABI of the B200 (sm_100a) IEGMN forward engine.
+ *
+ * Drop-in boundary for the ONE hot path of octavian-ganea/equidock_public:
+ *   src/model/rigid_docking_model.py  IEGMN_Layer.forward (:189-352), IEGMN.forward (:451-602),
+ *   Rigid_Body_Docking_Net.forward (:642-692).
+ * The reference has no FFI of its own (pure Python over torch/DGL); these entry points are what a
+ * binding for that path would call.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain C: device pointers + sizes + a cudaStream_t passed as void*; no torch types.
+ *   - the CALLER owns every buffer (inputs, outputs, workspace); the library never allocates,
+ *     never synchronises the stream, keeps no global mutable state (thread-safe per stream).
+ *   - every function returns 0 on success or a negative EQD_ERR_* code; kernel launch errors are
+ *     returned as -(1000 + cudaError_t).
+ *   - all matrices are row-major fp32 unless stated; coordinates inside the engine are fp64.
+ *
+ * Node / edge numbering of a batch of B protein pairs (mirrors dgl.batch of the reference's
+ * heterograph, src/utils/train_utils.py:61-100): ligand nodes of pair 0..B-1, then receptor nodes
+ * of pair 0..B-1 ("global node id").  Segment s < B is the ligand of pair s, segment B+s its
+ * receptor; seg_ptr[2B+1] are global node offsets.  Edges are sorted by destination (CSR): edge e
+ * = (col_src[e] -> the node whose row contains e), meaning "src is one of dst's k nearest
+ * neighbours" (src/utils/protein_utils.py:339-346).
+ */
+#ifndef EQD_IEGMN_H
+#define EQD_IEGMN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EQD_ABI_VERSION 1
+
+#define EQD_EDGE_FEATS 27     /* input_edge_feats_dim, protein_utils.py:71-86 + :373-389 */
+#define EQD_N_RBF 15          /* all_sigmas_dist = 1.5**s, rigid_docking_model.py:116 */
+#define EQD_HID 64            /* iegmn_lay_hid_dim (out_feats_dim) */
+#define EQD_H0 69             /* residue_emb_dim 64 + 5 surface features, :382-388 */
+#define EQD_H0_PAD 72         /* row stride of padded 69-wide tensors */
+#define EQD_N_RES_TYPES 21    /* nn.Embedding(21, 64), :382 */
+#define EQD_HEADS 50          /* num_att_heads */
+#define EQD_TILE_ROWS 128     /* rows (edges / nodes) per CTA tile */
+
+enum {
+  EQD_OK = 0,
+  EQD_ERR_BAD_ARG = -1,       /* null pointer / size out of range */
+  EQD_ERR_UNSUPPORTED = -2,   /* e.g. layer width other than 64 / 69, in-degree > 128 */
+  EQD_ERR_WORKSPACE = -3      /* workspace smaller than eqd_workspace_bytes() */
+};
+
+/* per-pair status bits written by eqd_kabsch_apply (rigid_docking_model.py:570-584) */
+#define EQD_STATUS_SVD_DEGENERATE 1  /* guard :574 fired: min S < 1e-3 or min |S_i^2-S_j^2| < 1e-2 */
+#define EQD_STATUS_NAN 2             /* assert :570 would have failed */
+/* global status bit (status[n_pairs]) */
+#define EQD_STATUS_DEGREE_OVERFLOW 4 /* some node has more than max_in_degree in-edges */
+
+/* ---- batch topology (all pointers device memory) ------------------------------------------ */
+typedef struct eqd_graph {
+  int32_t n_pairs;            /* B */
+  int32_t n_nodes;            /* sum N_l + sum N_r */
+  int32_t n_lig_nodes;        /* sum N_l */
+  int32_t n_edges;            /* sum E_l + sum E_r */
+  int32_t n_lig_edges;        /* sum E_l */
+  int32_t max_in_degree;      /* upper bound on in-degree (graph_max_neighbor, 10); <= 128 */
+  const int32_t* seg_ptr;     /* [2B+1] global node offsets of the 2B segments */
+  const int32_t* row_ptr;     /* [n_nodes+1] CSR-by-destination edge offsets */
+  const int32_t* col_src;     /* [n_edges] global source node of every edge */
+  const int32_t* edge_dst;    /* [n_edges] global destination node of every edge */
+  const float* he_lig;        /* [n_lig_edges][27] edges['ll'].data['he'] */
+  const float* he_rec;        /* [n_edges-n_lig_edges][27] edges['rr'].data['he'] */
+  int32_t n_node_tiles;       /* number of (segment, first node) tiles of <=128 nodes */
+  const int32_t* node_tiles;  /* [n_node_tiles][2] = {segment, first global node} */
+} eqd_graph;
+
+/* ---- one IEGMN_Layer's parameters, repacked k-major (in-dim x out-dim) --------------------- */
+/* dh = layer input width (69 for layer 0, else 64), dhp = 72 / 64 its padded width.
+ * "k-major" = element [k][n] multiplies input feature k into output n, i.e. the transpose of
+ * the nn.Linear weight in the reference state_dict; padded rows/cols are zero.               */
+typedef struct eqd_layer_params {
+  int32_t dh, dhp;
+  /* node projections of h (one GEMM): column groups
+   *   [0,64)            Psrc = h . edge_mlp.0.weight[:, 0:dh]^T
+   *   [64,128)          Pdst = h . edge_mlp.0.weight[:, dh:2dh]^T + edge_mlp.0.bias
+   *   [128,128+dhp)     Q = LeakyReLU(h . att_mlp_Q.0.weight^T)
+   *   [128+dhp,+2dhp)   K = LeakyReLU(h . att_mlp_K.0.weight^T)
+   *   [128+2dhp,+3dhp)  V = h . att_mlp_V.0.weight^T                                        */
+  const float* w_proj;        /* [dhp][128+3*dhp] */
+  const float* b_proj;        /* [128+3*dhp] */
+  const float* w_edge1;       /* [44][64]: rows 0..26 he, 27..41 rbf, 42..43 zero (edge_mlp.0.weight[:, 2dh:]^T) */
+  const float* edge_ln_g;     /* [64] edge_mlp.3.weight */
+  const float* edge_ln_b;     /* [64] edge_mlp.3.bias */
+  const float* w_edge2;       /* [64][64] edge_mlp.4.weight^T */
+  const float* b_edge2;       /* [64] */
+  const float* w_coor1;       /* [64][64] coors_mlp.0.weight^T */
+  const float* b_coor1;       /* [64] */
+  const float* w_coor2;       /* [64] coors_mlp.4.weight */
+  float b_coor2;              /* coors_mlp.4.bias */
+  const float* w_node1;       /* [dhp+64+dhp+72][dhp] node_mlp.0.weight^T, row blocks [h | aggr_msg | mu | h0] */
+  const float* b_node1;       /* [dhp] */
+  const float* node_ln_g;     /* [dhp] node_mlp.3.weight (pad 0) */
+  const float* node_ln_b;     /* [dhp] */
+  const float* w_node2;       /* [dhp][64] node_mlp.4.weight^T */
+  const float* b_node2;       /* [64] */
+  float skip_weight_h;        /* args['skip_weight_h'] (applied only when dh == 64, :332-337) */
+  float x_connection_init;    /* args['x_connection_init'] (:286-292) */
+  float leaky_slope;          /* args['leakyrelu_neg_slope'] */
+} eqd_layer_params;
+
+/* ---- keypoint read-out parameters (IEGMN.__init__ :427-438), reference layouts ------------- */
+typedef struct eqd_head_params {
+  const float* w_mean;        /* [64][64] mlp_h_mean_ROT.0.weight^T (k-major) */
+  const float* b_mean;        /* [64] */
+  const float* w_key;         /* [3200][64] att_mlp_key_ROT.0.weight, as in the state_dict */
+  const float* w_query;       /* [3200][64] att_mlp_query_ROT.0.weight, as in the state_dict */
+  float leaky_slope;
+} eqd_head_params;
+
+int eqd_abi_version(void);
+
+/* Bytes of scratch the layer / head entry points need for this graph (host-side arithmetic). */
+size_t eqd_workspace_bytes(int32_t n_nodes, int32_t n_node_tiles, int32_t n_pairs);
+
+/* Input stage, IEGMN.forward :452-471.
+ *   h0[n][72]  = [Embedding(res_feat.long()) (64) | log(mu_r_norm) (5) | 0 0 0]
+ *   x64[n][3]  = ligand new_x / receptor x, widened to fp64                                  */
+int eqd_embed(const eqd_graph* g, const float* emb /*[21][64]*/,
+              const float* res_feat_lig, const float* res_feat_rec,   /* [N][1] fp32-encoded ints */
+              const float* mu_lig, const float* mu_rec,               /* [N][5] */
+              const float* x_lig /* new_x */, const float* x_rec /* x */, /* [N][3] */
+              float* h0, double* x64, void* stream);
+
+/* Node projections for a layer (see eqd_layer_params.w_proj): proj[n][128+3*dhp]. */
+int eqd_project(const eqd_graph* g, const eqd_layer_params* p, const float* h, int32_t ldh,
+                float* proj, void* stream);
+
+/* Edge stage of IEGMN_Layer.forward (:204-237, 263-292): RBF, edge MLP, coordinate MLP, mean
+ * aggregation at the destination, coordinate update.
+ *   aggr[n][64] = mean_e msg_e ;  x_out[n] = eta*x_orig[n] + (1-eta)*x_in[n] + mean_e x_rel*phi  */
+int eqd_edge_stage(const eqd_graph* g, const eqd_layer_params* p, const float* proj,
+                   const double* x_in, const double* x_orig, float* aggr, double* x_out,
+                   int32_t* status /* [n_pairs+1] */, void* stream);
+
+/* Node stage (:244-256, 319-349): segmented cross attention mu = softmax(q k^T) v over the partner
+ * protein, node MLP + LayerNorm + skip -> h_out[n][64]; if p_next != NULL also the next layer's
+ * projections (fused eqd_project on h_out) into proj_next.                                    */
+int eqd_node_stage(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next,
+                   const float* h_in, int32_t ldh, const float* h0, const float* proj,
+                   const float* aggr, float* h_out, float* proj_next, void* stream);
+
+/* One whole IEGMN_Layer.forward = eqd_edge_stage + eqd_node_stage (proj must hold this layer's
+ * projections on entry; holds the next layer's on exit when p_next != NULL).                  */
+int eqd_iegmn_layer_forward(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next,
+                            const float* h_in, int32_t ldh, const float* h0,
+                            const double* x_in, const double* x_orig,
+                            float* proj, float* proj_next, float* aggr,
+                            float* h_out, double* x_out, int32_t* status, void* stream);
+
+/* Keypoint read-out (IEGMN.forward :521-567): mean-pooled queries, 50-head attention over each
+ * protein's nodes, keypoints Y (fp64 [2B][50][3], segment order), their means and the 3x3
+ * covariance A = (Y_rec - mean)^T (Y_lig - mean) per pair (cov[B][9], ymean[2B][3]).        */
+int eqd_keypoints(const eqd_graph* g, const eqd_head_params* hp, const float* h /*[n][64]*/,
+                  const double* x /*[n][3] last-layer coords*/, void* workspace, size_t workspace_bytes,
+                  double* keypts, double* ymean, double* cov, void* stream);
+
+/* Kabsch + rigid transform (:571-589, 657-665): SVD of cov, guard test, T = U diag(1,1,sign det A) V^T,
+ * b = ymean_rec - T ymean_lig; ligand_out[n] = T new_x[n] + b for every ligand node.
+ * Outputs fp32 (what the reference returns): rot[B][9], trans[B][3], ligand_out[n_lig][3];
+ * sing[B][3] fp64 singular values; status[B] gets EQD_STATUS_* bits (caller zero-initialises).
+ * pair_mask: NULL = all pairs, else only pairs with pair_mask[b] != 0 are (re)computed.       */
+int eqd_kabsch_apply(const eqd_graph* g, const double* cov, const double* ymean, const float* x_lig_in,
+                     const int32_t* pair_mask, float* rot, float* trans, float* ligand_out,
+                     double* sing, int32_t* status, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EQD_IEGMN_H */
