@@ -167,6 +167,12 @@ def _sorted_copy(plan_args):
 class IEGMNEngine:
     """Runs the IEGMN stack + keypoints + Kabsch for one plan on the current CUDA stream."""
 
+    @staticmethod
+    def launches_per_forward(n_layers: int) -> int:
+        """Kernels of csrc/ launched by one forward: embed, project, (edge, node) x L, head_mean,
+        tile_ptr, keypoints, keypoint_cov, kabsch_apply."""
+        return 2 + 2 * n_layers + 5
+
     def __init__(self, device):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
@@ -174,7 +180,8 @@ class IEGMNEngine:
         self.lib = nat.load()
 
     def forward(self, plan: GraphPlan, emb: torch.Tensor, layers: List[PackedLayer], head: PackedHead,
-                res_l, res_r, mu_l, mu_r, x_l, x_r, check_status: bool = True, log=None) -> Dict[str, torch.Tensor]:
+                res_l, res_r, mu_l, mu_r, x_l, x_r, check_status: bool = True, log=None,
+                stage_timer=None) -> Dict[str, torch.Tensor]:
         lib, dev = self.lib, self.device
         g = C.byref(plan.struct)
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -199,10 +206,22 @@ class IEGMNEngine:
         h_out, x_out = ha, xa
         for li, lay in enumerate(layers):
             nxt = layers[li + 1] if li + 1 < len(layers) else None
-            nat.check(lib.eqd_iegmn_layer_forward(
-                g, C.byref(lay.struct), C.byref(nxt.struct) if nxt is not None else None,
-                nat.ptr(h_in), ldh, nat.ptr(h0), nat.ptr(x_in), nat.ptr(x0), nat.ptr(pa), nat.ptr(pb),
-                nat.ptr(aggr), nat.ptr(h_out), nat.ptr(x_out), nat.ptr(status), st), f'eqd_iegmn_layer_forward[{li}]')
+            lp = C.byref(lay.struct)
+            lpn = C.byref(nxt.struct) if nxt is not None else None
+            if stage_timer is None:
+                nat.check(lib.eqd_iegmn_layer_forward(
+                    g, lp, lpn, nat.ptr(h_in), ldh, nat.ptr(h0), nat.ptr(x_in), nat.ptr(x0), nat.ptr(pa), nat.ptr(pb),
+                    nat.ptr(aggr), nat.ptr(h_out), nat.ptr(x_out), nat.ptr(status), st),
+                    f'eqd_iegmn_layer_forward[{li}]')
+            else:  # same two launches, bracketed by CUDA events on the launching stream
+                stage_timer.begin('edge_stage', li)
+                nat.check(lib.eqd_edge_stage(g, lp, nat.ptr(pa), nat.ptr(x_in), nat.ptr(x0), nat.ptr(aggr),
+                                             nat.ptr(x_out), nat.ptr(status), st), f'eqd_edge_stage[{li}]')
+                stage_timer.end('edge_stage', li)
+                stage_timer.begin('node_stage', li)
+                nat.check(lib.eqd_node_stage(g, lp, lpn, nat.ptr(h_in), ldh, nat.ptr(h0), nat.ptr(pa), nat.ptr(aggr),
+                                             nat.ptr(h_out), nat.ptr(pb), st), f'eqd_node_stage[{li}]')
+                stage_timer.end('node_stage', li)
             pa, pb = pb, pa
             h_in, ldh, x_in = h_out, nat.HID, x_out
             h_out = hb if h_out is ha else ha
@@ -223,7 +242,7 @@ class IEGMNEngine:
             nat.ptr(lig_out), nat.ptr(sing), nat.ptr(status), st), 'eqd_kabsch_apply')
         kab(None)
         out = {'ligand_coors': lig_out, 'keypts': keyp, 'rotation': rot, 'translation': trans, 'h': h_fin,
-               'x64': x_fin, 'cov': cov, 'sing': sing, 'status': status, 'unsorted': plan.unsorted}
+               'x64': x_fin, 'cov': cov, 'sing': sing, 'status': status, 'unsorted': plan.unsorted, 'kabsch': kab}
         if check_status:
             self.resolve_status(plan, out, kab, log)
         return out

@@ -142,13 +142,26 @@ class PairGraphBatch:
         g = PairGraphBatch(self._num_nodes,
                            {et: (s.to(device, non_blocking=non_blocking), d.to(device, non_blocking=non_blocking))
                             for et, (s, d) in self._edges.items()},
-                           {nt: v.to(device) for nt, v in self._batch_num_nodes.items()},
-                           {et: v.to(device) for et, v in self._batch_num_edges.items()})
+                           self._batch_num_nodes, self._batch_num_edges)  # counts stay on the host: no sync to read
         for nt in self.ntypes:
             g._ndata[nt] = {k: v.to(device, non_blocking=non_blocking) for k, v in self._ndata[nt].items()}
         for et in CANONICAL_ETYPES:
             g._edata[et] = {k: v.to(device, non_blocking=non_blocking) for k, v in self._edata[et].items()}
         return g
+
+    def pin_memory(self) -> 'PairGraphBatch':
+        """Page-locks every host tensor in place (for asynchronous H2D copies)."""
+        self._edges = {et: (s.pin_memory(), d.pin_memory()) for et, (s, d) in self._edges.items()}
+        for fr in list(self._ndata.values()) + list(self._edata.values()):
+            for k in list(fr.keys()):
+                fr[k] = fr[k].pin_memory()
+        return self
+
+    def nbytes(self) -> int:
+        tot = sum(s.numel() * s.element_size() + d.numel() * d.element_size() for s, d in self._edges.values())
+        for fr in list(self._ndata.values()) + list(self._edata.values()):
+            tot += sum(v.numel() * v.element_size() for v in fr.values())
+        return int(tot)
 
     def __repr__(self) -> str:
         return (f'PairGraphBatch(pairs={self.batch_size}, ligand_nodes={self._num_nodes[LIGAND]}, '

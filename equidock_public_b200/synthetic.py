@@ -36,7 +36,7 @@ def synthetic_protein(rng: np.random.Generator, n: int, k: int = 10):
             'x': x, 'mu_r_norm': rng.uniform(0.05, 1.0, size=(n, 5)).astype(np.float32)}
 
 
-def random_rigid(rng: np.random.Generator, translation_interval: float = 5.0):
+def random_rigid(rng: np.random.Generator, translation_interval: float = 5.0, dtype=np.float32):
     q = rng.normal(size=4)
     q /= np.linalg.norm(q)
     w, a, b, c = q
@@ -45,7 +45,7 @@ def random_rigid(rng: np.random.Generator, translation_interval: float = 5.0):
                   [2 * (a * c - b * w), 2 * (b * c + a * w), 1 - 2 * (a * a + b * b)]])
     t = rng.normal(size=3)
     t = t / np.linalg.norm(t) * rng.uniform(0, translation_interval)
-    return R.astype(np.float32), t.astype(np.float32)
+    return R.astype(dtype), t.astype(dtype)
 
 
 def synthetic_pair(rng: np.random.Generator, n_lig: int = 200, n_rec: int = 200, k: int = 10):

@@ -69,7 +69,7 @@ def main():
             o32 = rr.run_reference(m32, [pair], torch.float32)
             o64 = rr.run_reference(m64, [pair], torch.float64)
             R, t, resid = rr.golden_rigid_from_pdbs(ds, name)
-            lig_file, _, out_file = rr.test_pair_files(ds, name)
+            lig_file, rec_gt_file, out_file = rr.test_pair_files(ds, name)
             P, Q = rr.read_all_atoms(lig_file), rr.read_all_atoms(out_file)
             rerun = (o32['rotation'][0].astype(np.float64) @ P.T).T + o32['translation'][0].astype(np.float64)
             for side, d in (('lig', pair[0]), ('rec', pair[1])):
@@ -82,6 +82,12 @@ def main():
                     blob[f'{name}/{tag}/{k}'] = o[k].astype(dt)
             blob[f'{name}/pdb/rotation'] = R
             blob[f'{name}/pdb/translation'] = t
+            # C-alpha traces for the reference's complex-RMSD metric (eval_pdb_outputset.py:40-78): input
+            # ligand, ground-truth ligand and receptor of the bound complex, in file order
+            gt_lig_file = rec_gt_file.replace('_r_b_COMPLEX', '_l_b_COMPLEX')
+            blob[f'{name}/ca/ligand_in'] = rr.read_ca_atoms(lig_file)
+            blob[f'{name}/ca/ligand_gt'] = rr.read_ca_atoms(gt_lig_file)
+            blob[f'{name}/ca/receptor_gt'] = rr.read_ca_atoms(rec_gt_file)
             summary[ds][name] = {
                 'n_ligand': int(pair[0]['x'].shape[0]), 'n_receptor': int(pair[1]['x'].shape[0]),
                 'e_ligand': int(pair[0]['src'].shape[0]), 'e_receptor': int(pair[1]['src'].shape[0]),

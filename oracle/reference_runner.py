@@ -179,6 +179,12 @@ def read_all_atoms(pdb_path) -> np.ndarray:
     return df[['x_coord', 'y_coord', 'z_coord']].to_numpy().astype(np.float64)
 
 
+def read_ca_atoms(pdb_path) -> np.ndarray:
+    from biopandas.pdb import PandasPdb
+    df = PandasPdb().read_pdb(pdb_path).df['ATOM']
+    return df[df['atom_name'] == 'CA'][['x_coord', 'y_coord', 'z_coord']].to_numpy().astype(np.float64)
+
+
 def golden_rigid_from_pdbs(dataset: str, name: str):
     """(R*, t*) of the reference's shipped output PDB w.r.t. its input PDB, by all-atom Kabsch;
     returns (R, t, residual_max)."""

@@ -39,6 +39,8 @@ def load_pairs(ds):
                                                                      'h_out_ligand', 'h_out_receptor']}
                    for tag in ('ref32', 'ref64')}
         outs[n]['pdb'] = {'rotation': z[f'{n}/pdb/rotation'], 'translation': z[f'{n}/pdb/translation']}
+        if f'{n}/ca/ligand_in' in z:
+            outs[n]['ca'] = {k: z[f'{n}/ca/{k}'] for k in ('ligand_in', 'ligand_gt', 'receptor_gt')}
     _CACHE[ds] = (names, pairs, outs, z)
     return _CACHE[ds]
 

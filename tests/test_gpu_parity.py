@@ -1,0 +1,292 @@
+"""GPU (B200) parity tests: the CUDA engine, called through the reference-facing module and the C ABI,
+against (a) outputs of the reference's unmodified module in fp64 on its shipped test inputs/checkpoints
+(tests/golden), (b) the numpy fp64 oracle on seeded synthetic / ragged / edge-case graphs, and
+(c) size-independent properties at the bench's full size.
+
+Tolerance (north_star: 1e-4 on predicted coordinates): per pair
+    max|coords - fp64 reference| <= max(1e-4, |reference fp32 - reference fp64|)
+i.e. never worse than the reference's own fp32 evaluation of itself (SURVEY 0, 7 'hard parts').
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import golden_io as gio
+import iegmn_oracle as orc
+from equidock_public_b200 import _native as nat
+from equidock_public_b200 import hetero_graph as hg
+from equidock_public_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+COORD_TOL = 1e-4          # Angstrom, north_star
+ROT_TOL = 3e-5            # rotation matrix entries (reference fp32 vs fp64 differs by <= 2.6e-5)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope='module')
+def models(cuda_device):
+    return {ds: gio.build_model(ds, cuda_device) for ds in ('db5', 'dips')}
+
+
+def _all_cases():
+    out = []
+    for ds in ('db5', 'dips'):
+        out += [(ds, n) for n in gio.load_pairs(ds)[0]]
+    return out
+
+
+@pytest.mark.parametrize('ds,name', _all_cases())
+def test_golden_pair_matches_reference_fp64(ds, name, models, cuda_device):
+    names, pairs, outs, _ = gio.load_pairs(ds)
+    g = gio.make_batch([pairs[name]], cuda_device)
+    coors, kp_l, kp_r, rot, trans = models[ds](g, epoch=0)
+    r64, r32 = outs[name]['ref64'], outs[name]['ref32']
+    yard = np.abs(r32['ligand_coors'] - r64['ligand_coors']).max()
+    err = np.abs(_np(coors[0]) - r64['ligand_coors']).max()
+    assert err <= max(COORD_TOL, yard), (err, yard)
+    assert np.abs(_np(rot[0]) - r64['rotation']).max() <= ROT_TOL
+    assert np.abs(_np(trans[0]) - r64['translation']).max() <= max(COORD_TOL, 3 * yard)
+    assert trans[0].shape == (1, 3) and rot[0].shape == (3, 3) and kp_l[0].shape == (50, 3)
+    ky = max(np.abs(r32['keypts_ligand'] - r64['keypts_ligand']).max(), np.abs(r32['keypts_receptor'] - r64['keypts_receptor']).max())
+    assert np.abs(_np(kp_l[0]) - r64['keypts_ligand']).max() <= max(2e-4, ky)
+    assert np.abs(_np(kp_r[0]) - r64['keypts_receptor']).max() <= max(2e-4, ky)
+    # side effects on the graph (rigid_docking_model.py:507-510)
+    hy = np.abs(r32['h_out_ligand'] - r64['h_out_ligand']).max()
+    assert np.abs(_np(g.nodes['ligand'].data['hv_iegmn_out']) - r64['h_out_ligand']).max() <= max(2e-5, 2 * hy)
+    assert np.abs(_np(g.nodes['receptor'].data['hv_iegmn_out']) - r64['h_out_receptor']).max() <= max(2e-5, 2 * hy)
+    xy = np.abs(r32['x_out_receptor'] - r64['x_out_receptor']).max()
+    assert np.abs(_np(g.nodes['receptor'].data['x_iegmn_out']) - r64['x_out_receptor']).max() <= max(1e-3, 2 * xy)
+    # golden (R*, t*) recovered from the reference's shipped output PDB (3-decimal rounding)
+    lig_in = pairs[name][0]['new_x'].astype(np.float64)
+    pdb = (outs[name]['pdb']['rotation'] @ lig_in.T).T + outs[name]['pdb']['translation']
+    assert np.abs(pdb - _np(coors[0])).max() < 3e-3
+
+
+@pytest.mark.parametrize('ds', ['db5', 'dips'])
+def test_ragged_batch_equals_per_pair_bitwise(ds, models, cuda_device):
+    """Pairs never interact (block-diagonal mask, :61-78): a batched call must reproduce every B=1 call."""
+    names, pairs, outs, _ = gio.load_pairs(ds)
+    batched = models[ds](gio.make_batch([pairs[n] for n in names], cuda_device), epoch=0)
+    for i, n in enumerate(names):
+        single = models[ds](gio.make_batch([pairs[n]], cuda_device), epoch=0)
+        for a, b in zip(batched, single):
+            assert torch.equal(a[i], b[0]), n
+        assert np.abs(_np(batched[0][i]) - outs[n]['ref64']['ligand_coors']).max() <= max(
+            COORD_TOL, np.abs(outs[n]['ref32']['ligand_coors'] - outs[n]['ref64']['ligand_coors']).max())
+
+
+@pytest.mark.parametrize('ds', ['db5', 'dips'])
+def test_complex_rmsd_matches_reference(ds, models, cuda_device):
+    """The metric of BASELINE.json ('complex RMSD vs ref'), src/utils/eval.py:19-42: the C-RMSD of our prediction
+    equals the C-RMSD of the reference's prediction for every fixture complex."""
+    names, pairs, outs, _ = gio.load_pairs(ds)
+    for n in names:
+        ca = outs[n]['ca']
+        _, _, _, rot, trans = models[ds](gio.make_batch([pairs[n]], cuda_device), epoch=0)
+        R, t = _np(rot[0]).astype(np.float64), _np(trans[0]).astype(np.float64)
+        ours = orc.complex_rmsd((R @ ca['ligand_in'].T).T + t, ca['receptor_gt'], ca['ligand_gt'], ca['receptor_gt'])
+        R0, t0 = outs[n]['ref64']['rotation'], outs[n]['ref64']['translation']
+        ref = orc.complex_rmsd((R0 @ ca['ligand_in'].T).T + t0, ca['receptor_gt'], ca['ligand_gt'], ca['receptor_gt'])
+        assert abs(ours - ref) < 1e-4, (n, ours, ref)
+
+
+def _layer_inputs(ds, name, li):
+    """Inputs of layer `li` for one golden pair, from the oracle's trace (fp64)."""
+    names, pairs, outs, _ = gio.load_pairs(ds)
+    sd, args = gio.load_checkpoint(ds), gio.load_args(ds)
+    cfg = orc.OracleConfig.from_args(args)
+    cfg_short = orc.OracleConfig(li, cfg.skip_weight_h, cfg.x_connection_init, cfg.slope, cfg.num_att_heads)
+    st = orc.forward_pair(sd, cfg_short, *pairs[name], head=False)     # state after li layers
+    return pairs[name], st, sd, cfg
+
+
+@pytest.mark.parametrize('ds,name,li', [('dips', 'cf_5cff.pdb2_1.dill', 0), ('dips', 'cf_5cff.pdb2_1.dill', 3),
+                                        ('db5', '1ZHI', 0), ('db5', '1ZHI', 2), ('dips', 'hm_4hm1.pdb1_0.dill', 7)])
+def test_single_layer_operator_matches_oracle(ds, name, li, models, cuda_device):
+    """IEGMN_Layer.forward with the reference's signature (rigid_docking_model.py:189-352), layer-0 widths
+    (69/180/271) and layer>=1 widths, against the oracle's layer on the same inputs."""
+    pair, st, sd, cfg = _layer_inputs(ds, name, li)
+    lig, rec = pair
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    emb = f64(sd['iegmn_original.residue_emb_layer.weight'])
+    h0 = [np.concatenate([emb[np.asarray(s['res_feat']).reshape(-1).astype(int)], np.log(f64(s['mu_r_norm']))], 1)
+          for s in (lig, rec)]
+    sides = []
+    for s, h0s, x, h, ck in ((lig, h0[0], st['x_out_ligand'], st['h_out_ligand'], 'new_x'),
+                             (rec, h0[1], st['x_out_receptor'], st['h_out_receptor'], 'x')):
+        sides.append({'x': x, 'x_orig': f64(s[ck]), 'h': h if li > 0 else h0s, 'h0': h0s, 'he': f64(s['he']),
+                      'src': np.asarray(s['src']).astype(np.int64), 'dst': np.asarray(s['dst']).astype(np.int64)})
+    p = orc.LayerParams(sd, f'iegmn_original.iegmn_layers.{li}.', np.float64)
+    (xl, hl), (xr, hr) = orc.iegmn_layer(p, cfg, sides)
+    layer = models[ds].iegmn_original.iegmn_layers[li]
+    g = gio.make_batch([pair], cuda_device)
+    t = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32)).to(cuda_device)
+    out = layer(g, t(sides[0]['x']), t(sides[0]['h']), t(h0[0]), g.edges['ll'].data['he'], t(sides[0]['x_orig']),
+                t(sides[1]['x']), t(sides[1]['h']), t(h0[1]), g.edges['rr'].data['he'], t(sides[1]['x_orig']))
+    scale_x = max(1.0, np.abs(xl).max(), np.abs(xr).max())
+    assert np.abs(_np(out[1]) - hl).max() < 2e-5 and np.abs(_np(out[3]) - hr).max() < 2e-5
+    # inputs were rounded to fp32 on the way in: coordinates agree to fp32 resolution of their magnitude
+    assert np.abs(_np(out[0]) - xl).max() < 4e-6 * scale_x + 1e-5
+    assert np.abs(_np(out[2]) - xr).max() < 4e-6 * scale_x + 1e-5
+
+
+def _random_model(cuda_device, n_layers, shared, seed):
+    args = gio.load_args('db5')
+    args.update({'iegmn_n_lays': n_layers, 'shared_layers': shared, 'skip_weight_h': 0.6})
+    torch.manual_seed(seed)
+    from equidock_public_b200.rigid_docking_model import Rigid_Body_Docking_Net
+    args['device'] = cuda_device
+    model = Rigid_Body_Docking_Net(args, log=print)
+    with torch.no_grad():   # non-trivial biases and LayerNorm affine parameters
+        for name, p in model.named_parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.3, 0.3)
+                if name.endswith('.3.weight'):
+                    p.add_(1.0)
+    return model.to(cuda_device).eval(), args
+
+
+@pytest.mark.parametrize('sizes,k', [([(3, 2), (12, 15)], 10), ([(9, 40), (33, 5), (128, 129), (2, 2)], 10),
+                                      ([(257, 64), (70, 300)], 6), ([(20, 20)] * 7, 3)])
+def test_ragged_synthetic_graphs_vs_oracle(sizes, k, cuda_device):
+    """Seeded random-init weights (default nn init, 3-layer unshared), ragged sizes incl. N < k+1 (in-degree < 10),
+    N_l != N_r, tile boundaries (128/129, 257): engine == numpy fp64 oracle."""
+    model, args = _random_model(cuda_device, 3, False, seed=sum(a + b for a, b in sizes))
+    rng = np.random.default_rng(len(sizes) * 100 + k)
+    pairs = [synthetic.synthetic_pair(rng, a, b, k) for a, b in sizes]
+    coors, kp_l, kp_r, rot, trans = model(gio.make_batch(pairs, cuda_device), epoch=0)
+    sd = {kk: _np(v) for kk, v in model.state_dict().items()}
+    cfg = orc.OracleConfig.from_args(args)
+    for i, (lig, rec) in enumerate(pairs):
+        ref = orc.forward_pair(sd, cfg, lig, rec, rand_diag=iter(np.full((12, 3), 0.5)))
+        if ref['kabsch']['flagged']:   # rank-deficient keypoint clouds (e.g. 2 residues): random branch, see the guard test
+            continue
+        scale = max(1.0, float(np.abs(ref['ligand_coors']).max()) / 100.0)
+        assert np.abs(_np(coors[i]) - ref['ligand_coors']).max() <= 2e-4 * scale, (i, sizes[i])
+        assert np.abs(_np(rot[i]) - ref['rotation']).max() <= 5e-5
+
+
+def test_shared_layer_5_layer_model_and_in_degree_zero(cuda_device):
+    """shared_layers=True (DB5 checkpoint structure) + nodes with NO in-edges (mean aggregation -> 0, DGL
+    semantics, :274-283) + isolated source-only nodes."""
+    names, pairs, outs, _ = gio.load_pairs('db5')
+    lig, rec = [dict(d) for d in pairs['1QA9']]
+    keep = lig['dst'] >= 7                    # nodes 0..6 lose all their in-edges
+    for key in ('src', 'dst', 'he'):
+        lig[key] = lig[key][keep]
+    model = gio.build_model('db5', cuda_device)
+    coors, _, _, rot, _ = model(gio.make_batch([(lig, rec)], cuda_device), epoch=0)
+    ref = orc.forward_pair(gio.load_checkpoint('db5'), orc.OracleConfig.from_args(gio.load_args('db5')), lig, rec)
+    assert np.abs(_np(coors[0]) - ref['ligand_coors']).max() < 2e-4
+    assert np.abs(_np(rot[0]) - ref['rotation']).max() < ROT_TOL
+
+
+def test_unsorted_edges_take_the_sorting_path(models, cuda_device):
+    names, pairs, outs, _ = gio.load_pairs('dips')
+    lig, rec = [dict(d) for d in pairs[names[1]]]
+    perm = np.random.default_rng(0).permutation(lig['src'].shape[0])
+    for key in ('src', 'dst', 'he'):
+        lig[key] = lig[key][perm]
+    coors, *_ = models['dips'](gio.make_batch([(lig, rec)], cuda_device), epoch=0)
+    assert np.abs(_np(coors[0]) - outs[names[1]]['ref64']['ligand_coors']).max() < 1.5e-4
+
+
+def test_in_degree_overflow_is_reported(models, cuda_device):
+    names, pairs, outs, _ = gio.load_pairs('dips')
+    lig, rec = [dict(d) for d in pairs[names[0]]]
+    g = gio.make_batch([(lig, rec)], cuda_device)
+    model = gio.build_model('dips', cuda_device)
+    model.iegmn_original.graph_max_neighbor = 5          # true in-degree is 10 -> 12 nodes x 10 edges > tile
+    with pytest.raises(nat.NativeLibraryError):
+        model(g, epoch=0)
+
+
+def test_svd_guard_branch_replays_reference_host_loop(models, cuda_device):
+    """All receptor residues coincide => receptor keypoints coincide => A = 0 => the guard of :574 fires; the
+    host loop adds torch.rand(3,3)*eye (CPU generator) exactly like :578 until the guard passes."""
+    names, pairs, outs, _ = gio.load_pairs('dips')
+    lig, rec = [dict(d) for d in pairs[names[0]]]
+    rec['x'] = np.tile(rec['x'][:1], (rec['x'].shape[0], 1))
+    torch.manual_seed(1234)
+    coors, _, _, rot, trans = models['dips'](gio.make_batch([(lig, rec)], cuda_device), epoch=0)
+    torch.manual_seed(1234)
+    draws = iter([torch.rand(3, 3).diagonal().double().numpy() for _ in range(12)])
+    ref = orc.forward_pair(gio.load_checkpoint('dips'), orc.OracleConfig.from_args(gio.load_args('dips')), lig, rec,
+                           rand_diag=draws)
+    assert ref['kabsch']['flagged']
+    R = _np(rot[0]).astype(np.float64)
+    assert abs(np.linalg.det(R) - 1) < 1e-5 and np.abs(R @ R.T - np.eye(3)).max() < 1e-5
+    assert np.abs(R - ref['rotation']).max() < 1e-4
+    assert np.abs(_np(coors[0]) - ref['ligand_coors']).max() < 2e-3
+
+
+def test_equivariance_properties_on_engine(models, cuda_device):
+    """Size-independent properties (SURVEY 7 test 5): ligand-pose invariance, receptor-motion equivariance."""
+    names, pairs, outs, _ = gio.load_pairs('dips')
+    lig, rec = pairs[names[2]]
+    rng = np.random.default_rng(3)
+    Q, gvec = synthetic.random_rigid(rng, 20.0, dtype=np.float64)
+    base = _np(models['dips'](gio.make_batch([(lig, rec)], cuda_device), 0)[0][0])
+    lig2 = dict(lig)
+    lig2['new_x'] = ((Q @ lig['new_x'].astype(np.float64).T).T + gvec).astype(np.float32)
+    moved_l = _np(models['dips'](gio.make_batch([(lig2, rec)], cuda_device), 0)[0][0])
+    assert np.abs(moved_l - base).max() < 5e-4           # fp32 inputs are re-rounded by the motion
+    rec2 = dict(rec)
+    rec2['x'] = ((Q @ rec['x'].astype(np.float64).T).T + gvec).astype(np.float32)
+    moved_r = _np(models['dips'](gio.make_batch([(lig, rec2)], cuda_device), 0)[0][0])
+    assert np.abs(moved_r - ((Q @ base.astype(np.float64).T).T + gvec)).max() < 5e-4
+
+
+def test_full_size_batch_properties(models, cuda_device):
+    """BASELINE workload shape (200+200, k=10, 8 layers) at batch 64: finite, proper rotations, batched == a
+    sampled per-pair call bit-for-bit, and sampled pairs == oracle."""
+    pairs = synthetic.synthetic_batch(64, 200, 200, 10, seed=11)
+    coors, kp_l, kp_r, rot, trans = models['dips'](gio.make_batch(pairs, cuda_device), epoch=0)
+    R = torch.stack(rot).double()
+    assert torch.isfinite(torch.cat(coors)).all()
+    assert (torch.linalg.det(R) - 1).abs().max() < 1e-5
+    assert (R @ R.transpose(1, 2) - torch.eye(3, device=R.device, dtype=R.dtype)).abs().max() < 1e-5
+    sd, cfg = gio.load_checkpoint('dips'), orc.OracleConfig.from_args(gio.load_args('dips'))
+    for i in (0, 37, 63):
+        single = models['dips'](gio.make_batch([pairs[i]], cuda_device), epoch=0)
+        assert torch.equal(single[0][0], coors[i])
+        ref = orc.forward_pair(sd, cfg, *pairs[i])
+        assert np.abs(_np(coors[i]) - ref['ligand_coors']).max() < 2e-4, i
+
+
+def test_largest_case_2000_2000(models, cuda_device):
+    """BASELINE configs[4] shape: 2000+2000 residues (K/V streamed in 64-row chunks, 16 query tiles per protein)."""
+    pairs = synthetic.synthetic_batch(2, 2000, 2000, 10, seed=4)
+    coors, _, _, rot, _ = models['dips'](gio.make_batch(pairs, cuda_device), epoch=0)
+    ref = orc.forward_pair(gio.load_checkpoint('dips'), orc.OracleConfig.from_args(gio.load_args('dips')), *pairs[1])
+    assert np.abs(_np(rot[1]) - ref['rotation']).max() < 5e-5
+    assert np.abs(_np(coors[1]) - ref['ligand_coors']).max() < 5e-4
+
+
+def test_host_buffers_path_equals_device_path(models, cuda_device):
+    """The e2e route of bench.py: pinned host batch -> async H2D -> engine -> D2H."""
+    pairs = synthetic.synthetic_batch(5, 60, 45, 10, seed=2)
+    host = hg.batch_pairs(synthetic.to_torch_pairs(pairs)).pin_memory()
+    a = models['dips'](host.to(cuda_device, non_blocking=True), epoch=0)
+    b = models['dips'](gio.make_batch(pairs, cuda_device), epoch=0)
+    for x, y in zip(a[0], b[0]):
+        assert torch.equal(x, y)
+
+
+def test_c_abi_rejects_bad_arguments(cuda_device):
+    lib = nat.load()
+    g = nat.EqdGraph()
+    assert lib.eqd_embed(None, None, None, None, None, None, None, None, None, None, None) == -1
+    lp = nat.EqdLayerParams()
+    lp.dh, lp.dhp = 48, 48
+    one = torch.zeros(8, device=cuda_device)
+    assert lib.eqd_project(C.byref(g), C.byref(lp), nat.ptr(one), 48, nat.ptr(one), None) == -2
+    g.max_in_degree = 500
+    assert lib.eqd_edge_stage(C.byref(g), C.byref(lp), nat.ptr(one), nat.ptr(one), nat.ptr(one), nat.ptr(one),
+                              nat.ptr(one), nat.ptr(one), None) == -2

@@ -1,0 +1,109 @@
+"""CPU: pins the oracle (numpy fp64 restatement + its torch port) against outputs of the reference's own
+unmodified module on the reference's shipped test inputs / checkpoints (tests/golden, made by
+oracle/make_golden.py), and those against the reference's shipped golden output PDBs."""
+import numpy as np
+import pytest
+import torch
+
+import golden_io as gio
+import iegmn_oracle as orc
+import iegmn_oracle_torch as ot
+
+DATASETS = ('db5', 'dips')
+SMALL = {'db5': ['1QA9', '1ZHI', '1AVX'], 'dips': ['kq_1kq1.pdb1_2.dill', 'cf_5cff.pdb2_1.dill', 'aq_4aqa.pdb1_0.dill']}
+
+
+def _cases(which):
+    return [(ds, n) for ds in DATASETS for n in which[ds]]
+
+
+@pytest.mark.parametrize('ds,name', _cases(SMALL) + [('db5', '1H1V'), ('dips', 'hm_4hm1.pdb1_0.dill')])
+def test_numpy_oracle_equals_reference_fp64(ds, name):
+    names, pairs, outs, _ = gio.load_pairs(ds)
+    args = gio.load_args(ds)
+    out = orc.forward_pair(gio.load_checkpoint(ds), orc.OracleConfig.from_args(args), *pairs[name])
+    ref = outs[name]['ref64']
+    for k in gio.OUT_KEYS + ['x_out_ligand', 'x_out_receptor', 'h_out_ligand', 'h_out_receptor']:
+        assert np.abs(out[k] - ref[k]).max() < 1e-9, k
+    assert not out['kabsch']['flagged']
+
+
+def test_numpy_oracle_largest_pair_548_2000():
+    names, pairs, outs, _ = gio.load_pairs('db5')
+    out = orc.forward_pair(gio.load_checkpoint('db5'), orc.OracleConfig.from_args(gio.load_args('db5')), *pairs['1N2C'])
+    assert np.abs(out['ligand_coors'] - outs['1N2C']['ref64']['ligand_coors']).max() < 1e-9
+
+
+@pytest.mark.parametrize('ds', DATASETS)
+def test_reference_rerun_reproduces_shipped_golden_pdbs(ds):
+    """The fixtures' fp32 re-run of the unmodified reference matches the shipped EQUIDOCK output PDBs to PDB
+    rounding (3 decimals), and the (R*, t*) recovered from those PDBs matches the model's (R, t)."""
+    names, pairs, outs, _ = gio.load_pairs(ds)
+    summ = gio.summary()[ds]
+    for n in names:
+        assert summ[n]['pdb_rigid_fit_residual'] < 1e-3          # shipped output is a rigid image of its input
+        assert summ[n]['rerun_fp32_vs_shipped_pdb_max_abs'] < 2e-3
+        lig_in = pairs[n][0]['new_x'].astype(np.float64)
+        pdb = (outs[n]['pdb']['rotation'] @ lig_in.T).T + outs[n]['pdb']['translation']
+        assert np.abs(pdb - outs[n]['ref64']['ligand_coors']).max() < 3e-3
+
+
+@pytest.mark.parametrize('ds', DATASETS)
+def test_batched_reference_equals_per_pair(ds):
+    """The reference's dense-masked batched path (rigid_docking_model.py:61-78) == per-pair evaluation, which
+    is what lets the oracle (and the engine) use segmented attention."""
+    names, pairs, outs, z = gio.load_pairs(ds)
+    for n in [str(x) for x in z['batched3/names']]:
+        for k in gio.OUT_KEYS:
+            assert np.abs(z[f'batched3/{n}/{k}'] - outs[n]['ref64'][k]).max() < 1e-9
+
+
+@pytest.mark.parametrize('ds,name', _cases(SMALL))
+def test_torch_port_equals_numpy_oracle(ds, name):
+    names, pairs, outs, _ = gio.load_pairs(ds)
+    args = gio.load_args(ds)
+    t64 = ot.TorchOracle(gio.load_checkpoint(ds), args['iegmn_n_lays'], args['skip_weight_h'], dtype=torch.float64)
+    out = t64.forward_pair(*pairs[name])
+    for k in gio.OUT_KEYS:
+        assert np.abs(out[k].numpy() - outs[name]['ref64'][k]).max() < 1e-9, k
+
+
+def test_torch_port_fp32_is_the_reference_fp32():
+    """Same op sequence as the reference => reproduces its fp32 rounding, not just its fp64 value."""
+    names, pairs, outs, _ = gio.load_pairs('db5')
+    args = gio.load_args('db5')
+    t32 = ot.TorchOracle(gio.load_checkpoint('db5'), args['iegmn_n_lays'], args['skip_weight_h'])
+    out = t32.forward_pair(*pairs['1AVX'])
+    assert np.abs(out['ligand_coors'].numpy() - outs['1AVX']['ref32']['ligand_coors']).max() < 2e-4
+
+
+def test_oracle_equivariance_properties():
+    """SURVEY 7 test 5: ligand pose invariance and receptor-motion equivariance of the predicted complex."""
+    from equidock_public_b200 import synthetic
+    rng = np.random.default_rng(5)
+    lig, rec = synthetic.synthetic_pair(rng, 40, 50)
+    sd, args = gio.load_checkpoint('db5'), gio.load_args('db5')
+    cfg = orc.OracleConfig.from_args(args)
+    base = orc.forward_pair(sd, cfg, lig, rec)['ligand_coors']
+    Q, g = synthetic.random_rigid(rng, 20.0, dtype=np.float64)
+    lig2 = dict(lig)
+    lig2['new_x'] = (Q.astype(np.float64) @ lig['new_x'].astype(np.float64).T).T + g
+    assert np.abs(orc.forward_pair(sd, cfg, lig2, rec)['ligand_coors'] - base).max() < 1e-8
+    rec2 = dict(rec)
+    rec2['x'] = (Q.astype(np.float64) @ rec['x'].astype(np.float64).T).T + g
+    moved = orc.forward_pair(sd, cfg, lig, rec2)['ligand_coors']
+    assert np.abs(moved - ((Q.astype(np.float64) @ base.T).T + g)).max() < 1e-8
+
+
+def test_oracle_svd_guard_branch():
+    """Perturbation loop of rigid_docking_model.py:574-584 with an injected random source."""
+    sd = gio.load_checkpoint('db5')
+    cfg = orc.OracleConfig.from_args(gio.load_args('db5'))
+    rng = np.random.default_rng(0)
+    h = rng.normal(size=(6, 64))
+    x = np.tile(rng.normal(size=(1, 3)), (6, 1))      # all nodes coincide -> keypoints coincide -> A = 0
+    with pytest.raises(RuntimeError):
+        orc.keypoints_and_kabsch(sd, cfg, h, x, h, x, np.float64)
+    T, b, *_ , info = orc.keypoints_and_kabsch(sd, cfg, h, x, h, x, np.float64,
+                                               rand_diag=iter([np.array([0.9, 0.5, 0.2])] * 3))
+    assert info['flagged'] and abs(np.linalg.det(T) - 1) < 1e-9
