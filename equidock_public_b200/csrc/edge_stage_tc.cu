@@ -1,0 +1,460 @@
+// Edge stage of IEGMN_Layer.forward (rigid_docking_model.py:204-237, 263-292) on the 5th-gen tensor
+// cores (tcgen05 / TMEM), fp32-accurate through a 3-way bf16 split of both operands ("bf16x6":
+// a*w ~ a0w0 + a0w1 + a1w0 + a0w2 + a1w1 + a2w0, fp32 accumulation in TMEM; measured error below a
+// plain fp32 FMA loop, see scripts/tc_probe.cu).
+//
+// One persistent CTA per SM, 2 warpgroups; each warpgroup owns one tile of <=128 edges at a time
+// (thread r <-> edge row r <-> TMEM lane r), the two run out of phase so one's MMA phase overlaps the
+// other's epilogue.  Per tile and warpgroup:
+//   he rows (cp.async.bulk -> smem staging, prefetched one tile ahead) + 15 RBFs
+//     -> [he|rbf] bf16x3 -> TMEM (tcgen05.st)                      A operand of GEMM1 (K=48)
+//   GEMM1 (18 tcgen05.mma, B = edge_mlp.0.weight[:, 2dh:] bf16x3 resident in smem)
+//     -> + gathered Psrc[src] + Pdst[dst] (cp.async into smem), LeakyReLU, LayerNorm (one row per
+//        thread: no shuffles) -> bf16x3 -> TMEM
+//   GEMM2 (24 mma) -> msg (+bias) -> fp32 tile in smem (mean aggregation) and bf16x3 -> TMEM
+//   GEMM3 (24 mma) -> LeakyReLU, dot w4 -> phi ; x' = eta x0 + (1-eta) x + mean(x_rel phi) in fp64.
+// Per-edge activations never leave the SM; weights are read from HBM/L2 once per CTA.
+#include "common.cuh"
+
+namespace eqd {
+
+#define TC_THREADS 256
+#define TC_MAX_TN 32          // destination nodes per tile (Pdst staging rows)
+#define TC_LD 68              // fp32 row stride of the staging / msg tile
+#define TC_W_BYTES 67584      // 3 splits x (6144 + 8192 + 8192)
+#define TC_W1_SPLIT 6144
+#define TC_W2_BASE 18432
+#define TC_W3_BASE 43008
+#define TC_W23_SPLIT 8192
+#define TC_HE_STAGE_FLOATS (EQD_TM * EQD_EDGE_FEATS + 16)
+
+struct TcWgSmem {                         // per warpgroup
+  float stage[EQD_TM * TC_LD];            // gathered Psrc rows, later the fp32 msg tile
+  float pdst[TC_MAX_TN * TC_LD];          // Pdst rows of the tile's destination nodes
+  float he[TC_HE_STAGE_FLOATS];           // raw he rows of the tile (bulk-copied, 16B-aligned chunks)
+  double xm[EQD_TM * 3];                  // x_rel * phi per edge
+  int src[2][EQD_TM];
+  int dst[2][EQD_TM];
+  int rp[2][TC_MAX_TN + 4];
+};
+
+struct TcSmem {
+  unsigned char w[TC_W_BYTES];            // bf16x3 weights, canonical K-major no-swizzle UMMA layout
+  TcWgSmem wg[2];
+  unsigned long long w_bar, mma_bar[2], he_bar[2];
+  unsigned int tmem_base;
+};
+
+struct EdgeConsts {                       // per-layer vectors, passed by value (constant bank operands)
+  float ln_g[64], ln_b[64], b2[64], b3[64], w4[64];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned addr = smem_u32(bar);
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src));
+}
+__device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major no-swizzle canonical B descriptor: LBO (K direction) = 1024 B, SBO (N direction) = 128 B
+__device__ __forceinline__ unsigned long long b_desc(unsigned saddr) {
+  return (unsigned long long)((saddr >> 4) & 0x3FFF) | ((unsigned long long)(1024 >> 4) << 16) |
+         ((unsigned long long)(128 >> 4) << 32) | (1ull << 46);
+}
+// D[128x64] (+)= A[tmem, 128x16 bf16] * B[smem desc, 64x16 bf16]^T
+__device__ __forceinline__ void umma_ts(unsigned d_tmem, unsigned a_tmem, unsigned long long bdesc, unsigned accum) {
+  const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc),
+      "r"(accum) : "memory");
+}
+// All 6 cross products of the bf16x3 splits, smallest terms first; A split s at a_base + s*a_split_cols.
+__device__ __forceinline__ void issue_gemm(unsigned d_tmem, unsigned a_base, unsigned a_split_cols, unsigned w_saddr,
+                                           unsigned w_split_bytes, int kblocks) {
+  const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};
+  unsigned accum = 0;
+#pragma unroll
+  for (int pr = 0; pr < 6; ++pr)
+    for (int kb = 0; kb < kblocks; ++kb) {
+      umma_ts(d_tmem, a_base + pa[pr] * a_split_cols + kb * 8, b_desc(w_saddr + pb[pr] * w_split_bytes + kb * 2048), accum);
+      accum = 1;
+    }
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- bf16x3 split of register tiles and TMEM stores / loads -------------------------------------
+__device__ __forceinline__ unsigned cvt_bf16x2(float hi, float lo) {
+  unsigned d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// (v0, v1) -> three packed bf16x2 words (v0 in the low half = even k)
+__device__ __forceinline__ void split3_pair(float v0, float v1, unsigned& p0, unsigned& p1, unsigned& p2) {
+  p0 = cvt_bf16x2(v1, v0);
+  float r0 = v0 - __uint_as_float(p0 << 16), r1 = v1 - __uint_as_float(p0 & 0xFFFF0000u);
+  p1 = cvt_bf16x2(r1, r0);
+  r0 -= __uint_as_float(p1 << 16);
+  r1 -= __uint_as_float(p1 & 0xFFFF0000u);
+  p2 = cvt_bf16x2(r1, r0);
+}
+__device__ __forceinline__ void tmem_st16(unsigned taddr, const unsigned (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+               "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const unsigned* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float* v) {
+  unsigned r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+      "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// 64 fp32 values of this thread's row -> bf16x3 -> TMEM A region (3 splits x 32 columns)
+__device__ __forceinline__ void store_row_split3(unsigned a_taddr, const float (&v)[64]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    unsigned p0[16], p1[16], p2[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) split3_pair(v[h * 32 + 2 * c], v[h * 32 + 2 * c + 1], p0[c], p1[c], p2[c]);
+    tmem_st16(a_taddr + h * 16, p0);
+    tmem_st16(a_taddr + 32 + h * 16, p1);
+    tmem_st16(a_taddr + 64 + h * 16, p2);
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ EdgeConsts cst,
+                     const float* __restrict__ proj, const double* __restrict__ x_in, const double* __restrict__ x_orig,
+                     float* __restrict__ aggr, double* __restrict__ x_out, int* __restrict__ status, int tn) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
+  const int tid = threadIdx.x, wg = tid >> 7, r = tid & 127, warp = tid >> 5;
+  TcWgSmem& W = S.wg[wg];
+  const int pw = 128 + 3 * p.dhp;
+  const int ntiles = (g.n_nodes + tn - 1) / tn;
+
+  // ---- one-time setup: TMEM, barriers, weights (one TMA bulk copy) -------------------------------
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&S.w_bar, 1);
+    mbar_init(&S.mma_bar[0], 1);
+    mbar_init(&S.mma_bar[1], 1);
+    mbar_init(&S.he_bar[0], 1);
+    mbar_init(&S.he_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&S.w_bar, TC_W_BYTES);
+    bulk_g2s(S.w, p.w_edge_tc, TC_W_BYTES, &S.w_bar);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem = S.tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)wg * 256;  // my lane quarter, my column half
+  const unsigned d_col = tmem;            // D: 64 columns
+  const unsigned a_col = tmem + 64;       // A: 3 splits x 32 columns
+  const unsigned tmem_wg = S.tmem_base + (unsigned)wg * 256;  // lane 0 address for the MMA issuer
+  mbar_wait(&S.w_bar, 0);
+  unsigned mma_phase = 0, he_phase = 0;
+  const unsigned w_saddr = smem_u32(S.w);
+
+  // Prefetch of a tile's indices + he rows.  Returns e0 / ne of that tile.
+  auto prefetch = [&](int tile, int buf, int& e0_out, int& ne_out, int& off_l, int& n_l, int& off_r) {
+    const int n0 = tile * tn, nn = min(tn, g.n_nodes - n0);
+    const int e0 = __ldg(g.row_ptr + n0), e1 = __ldg(g.row_ptr + n0 + nn);
+    const int ne = e1 - e0;
+    e0_out = e0;
+    ne_out = ne;
+    off_l = off_r = 0;
+    n_l = 0;
+    if (ne <= EQD_TM) {
+      if (r < ne) {
+        cp_async4(&W.src[buf][r], g.col_src + e0 + r);
+        cp_async4(&W.dst[buf][r], g.edge_dst + e0 + r);
+      }
+      if (r <= nn) cp_async4(&W.rp[buf][r], g.row_ptr + n0 + r);
+      // he rows: [e0, e1) split at the ligand/receptor array boundary; 16-byte aligned bulk copies
+      const int el0 = min(e0, g.n_lig_edges), el1 = min(e1, g.n_lig_edges);
+      n_l = el1 - el0;
+      unsigned bytes = 0;
+      long sl = 0, sr = 0;
+      unsigned bl = 0, br = 0;
+      if (n_l > 0) {
+        long b0 = (long)el0 * (EQD_EDGE_FEATS * 4), b1 = (long)el1 * (EQD_EDGE_FEATS * 4);
+        sl = b0 & ~15L;
+        bl = (unsigned)(((b1 + 15) & ~15L) - sl);
+        off_l = (int)((b0 - sl) >> 2);
+      }
+      const int nr = ne - n_l;
+      unsigned dst_r_off = (bl + 15u) & ~15u;  // receptor part lands after the ligand part
+      if (nr > 0) {
+        long b0 = (long)(e0 + n_l - g.n_lig_edges) * (EQD_EDGE_FEATS * 4), b1 = (long)(e1 - g.n_lig_edges) * (EQD_EDGE_FEATS * 4);
+        sr = b0 & ~15L;
+        br = (unsigned)(((b1 + 15) & ~15L) - sr);
+        off_r = (int)(dst_r_off >> 2) + (int)((b0 - sr) >> 2);
+      }
+      bytes = bl + br;
+      if (r == 0) {
+        mbar_expect_tx(&S.he_bar[wg], bytes);
+        if (bl) bulk_g2s(W.he, reinterpret_cast<const unsigned char*>(g.he_lig) + sl, bl, &S.he_bar[wg]);
+        if (br) bulk_g2s(reinterpret_cast<unsigned char*>(W.he) + dst_r_off, reinterpret_cast<const unsigned char*>(g.he_rec) + sr, br,
+                         &S.he_bar[wg]);
+      }
+    }
+    cp_async_commit();
+  };
+
+  int tile = blockIdx.x * 2 + wg;
+  const int tstride = gridDim.x * 2;
+  int buf = 0;
+  int e0 = 0, ne = 0, off_l = 0, n_l = 0, off_r = 0;
+  if (tile < ntiles) prefetch(tile, buf, e0, ne, off_l, n_l, off_r);
+
+  for (; tile < ntiles; tile += tstride) {
+    const int n0 = tile * tn, nn = min(tn, g.n_nodes - n0);
+    const bool has_next = tile + tstride < ntiles;
+    int e0n = 0, nen = 0, off_ln = 0, n_ln = 0, off_rn = 0;
+    if (ne > EQD_TM) {  // in-degree bound violated: flag, skip (uniform per warpgroup)
+      if (r == 0) atomicOr(status + g.n_pairs, EQD_STATUS_DEGREE_OVERFLOW);
+      cp_async_wait<0>();
+      wg_barrier(wg);
+      if (has_next) prefetch(tile + tstride, buf ^ 1, e0n, nen, off_ln, n_ln, off_rn);
+      e0 = e0n; ne = nen; off_l = off_ln; n_l = n_ln; off_r = off_rn; buf ^= 1;
+      continue;
+    }
+    // ---- S0/S1: indices ready; gathers; geometry; [he|rbf] -> TMEM ---------------------------------
+    cp_async_wait<0>();
+    wg_barrier(wg);
+    const bool valid = r < ne;
+    const int sn = valid ? W.src[buf][r] : 0, dn = valid ? W.dst[buf][r] : 0;
+    // gathers of the node projections into smem (coalesced 16B chunks, 16 lanes per row)
+    for (int idx = r; idx < EQD_TM * 16; idx += 128) {
+      int row = idx >> 4, c4 = idx & 15;
+      bool ok = row < ne;
+      int s_row = ok ? W.src[buf][row] : 0;
+      cp_async16(&W.stage[row * TC_LD + c4 * 4], proj + (long)s_row * pw + c4 * 4, ok);
+    }
+    for (int idx = r; idx < nn * 16; idx += 128) {
+      int row = idx >> 4, c4 = idx & 15;
+      cp_async16(&W.pdst[row * TC_LD + c4 * 4], proj + (long)(n0 + row) * pw + 64 + c4 * 4, true);
+    }
+    cp_async_commit();
+    double rx = 0.0, ry = 0.0, rz = 0.0;
+    {
+      float a1v[48];
+      if (valid) {
+        rx = x_in[(long)sn * 3 + 0] - x_in[(long)dn * 3 + 0];  // u_sub_v :204-205
+        ry = x_in[(long)sn * 3 + 1] - x_in[(long)dn * 3 + 1];
+        rz = x_in[(long)sn * 3 + 2] - x_in[(long)dn * 3 + 2];
+      }
+      mbar_wait(&S.he_bar[wg], he_phase);
+      he_phase ^= 1;
+      const float* hrow = W.he + (r < n_l ? off_l + r * EQD_EDGE_FEATS : off_r + (r - n_l) * EQD_EDGE_FEATS);
+#pragma unroll
+      for (int k = 0; k < EQD_EDGE_FEATS; ++k) a1v[k] = valid ? hrow[k] : 0.f;
+      const float nd2 = -(float)(rx * rx + ry * ry + rz * rz);  // :208-209
+      // exp(-d^2 / 1.5^q) :210 -- correctly rounded reciprocals of sigma (1.5^q is exact in fp32)
+      constexpr double kS[EQD_N_RBF] = {1.0, 1.5, 2.25, 3.375, 5.0625, 7.59375, 11.390625, 17.0859375, 25.62890625,
+                                        38.443359375, 57.6650390625, 86.49755859375, 129.746337890625,
+                                        194.6195068359375, 291.92926025390625};
+#pragma unroll
+      for (int q = 0; q < EQD_N_RBF; ++q) a1v[EQD_EDGE_FEATS + q] = valid ? expf(nd2 * (float)(1.0 / kS[q])) : 0.f;
+#pragma unroll
+      for (int k = 42; k < 48; ++k) a1v[k] = 0.f;
+      unsigned p0[24], p1[24], p2[24];
+#pragma unroll
+      for (int c = 0; c < 24; ++c) split3_pair(a1v[2 * c], a1v[2 * c + 1], p0[c], p1[c], p2[c]);
+      unsigned v16[16];
+#define EQD_ST24(base, arr)                      \
+  _Pragma("unroll") for (int c = 0; c < 16; ++c) v16[c] = arr[c]; \
+  tmem_st16(base, v16);                          \
+  tmem_st8(base + 16, arr + 16);
+      EQD_ST24(a_col, p0)
+      EQD_ST24(a_col + 32, p1)
+      EQD_ST24(a_col + 64, p2)
+#undef EQD_ST24
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    wg_barrier(wg);
+    // ---- GEMM1: [he|rbf] (K=48) x W1e ---------------------------------------------------------------
+    if (r == 0) {
+      tc_fence_after();
+      issue_gemm(tmem_wg, tmem_wg + 64, 32, w_saddr, TC_W1_SPLIT, 3);
+      umma_commit(&S.mma_bar[wg]);
+    }
+    // he staging and the other index buffer are free now: prefetch the next tile behind the MMAs
+    if (has_next) prefetch(tile + tstride, buf ^ 1, e0n, nen, off_ln, n_ln, off_rn);
+    mbar_wait(&S.mma_bar[wg], mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue 1: + Psrc[src] + Pdst[dst], LeakyReLU, LayerNorm -> bf16x3 -> TMEM ----------------
+    {
+      float v[64];
+      tmem_ld32(d_col, v);
+      tmem_ld32(d_col + 32, v + 32);
+      if (has_next) cp_async_wait<1>(); else cp_async_wait<0>();  // gathers landed (the newest group is the prefetch)
+      wg_barrier(wg);
+      const int dloc = valid ? dn - n0 : 0;
+      const float4* ps = reinterpret_cast<const float4*>(&W.stage[r * TC_LD]);
+      const float4* pd = reinterpret_cast<const float4*>(&W.pdst[dloc * TC_LD]);
+      float sum = 0.f;
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        float4 a = ps[c4], b = pd[c4];
+        float t0 = lrelu(v[c4 * 4 + 0] + a.x + b.x, p.leaky_slope), t1 = lrelu(v[c4 * 4 + 1] + a.y + b.y, p.leaky_slope);
+        float t2 = lrelu(v[c4 * 4 + 2] + a.z + b.z, p.leaky_slope), t3 = lrelu(v[c4 * 4 + 3] + a.w + b.w, p.leaky_slope);
+        v[c4 * 4 + 0] = t0; v[c4 * 4 + 1] = t1; v[c4 * 4 + 2] = t2; v[c4 * 4 + 3] = t3;
+        sum += (t0 + t1) + (t2 + t3);
+      }
+      const float mean = sum * (1.f / 64.f);
+      float q = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        float d = v[c] - mean;
+        q = fmaf(d, d, q);
+      }
+      const float rstd = 1.f / sqrtf(q * (1.f / 64.f) + 1e-5f);
+#pragma unroll
+      for (int c = 0; c < 64; ++c) v[c] = (v[c] - mean) * rstd * cst.ln_g[c] + cst.ln_b[c];
+      store_row_split3(a_col, v);
+    }
+    tc_fence_before();
+    wg_barrier(wg);  // A operand complete; everyone is done with the Psrc staging (it becomes the msg tile)
+    // ---- GEMM2: edge_mlp.4 -> msg ---------------------------------------------------------------------
+    if (r == 0) {
+      tc_fence_after();
+      issue_gemm(tmem_wg, tmem_wg + 64, 32, w_saddr + TC_W2_BASE, TC_W23_SPLIT, 4);
+      umma_commit(&S.mma_bar[wg]);
+    }
+    mbar_wait(&S.mma_bar[wg], mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+    {
+      float v[64];
+      tmem_ld32(d_col, v);
+      tmem_ld32(d_col + 32, v + 32);
+#pragma unroll
+      for (int c = 0; c < 64; ++c) v[c] += cst.b2[c];
+      float4* ms = reinterpret_cast<float4*>(&W.stage[r * TC_LD]);
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) ms[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+      store_row_split3(a_col, v);
+    }
+    tc_fence_before();
+    wg_barrier(wg);
+    // ---- GEMM3: coors_mlp.0 ; mean aggregation of msg overlaps the MMAs ---------------------------------
+    if (r == 0) {
+      tc_fence_after();
+      issue_gemm(tmem_wg, tmem_wg + 64, 32, w_saddr + TC_W3_BASE, TC_W23_SPLIT, 4);
+      umma_commit(&S.mma_bar[wg]);
+    }
+    for (int o = r; o < nn * 64; o += 128) {  // :280-283
+      int nd = o >> 6, c = o & 63;
+      int rs = W.rp[buf][nd] - e0, re = W.rp[buf][nd + 1] - e0;
+      float sum = 0.f;
+      for (int rr = rs; rr < re; ++rr) sum += W.stage[rr * TC_LD + c];
+      int deg = re - rs;
+      aggr[(long)(n0 + nd) * 64 + c] = deg > 0 ? sum / (float)deg : 0.f;
+    }
+    mbar_wait(&S.mma_bar[wg], mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+    {
+      float v[64];
+      tmem_ld32(d_col, v);
+      tmem_ld32(d_col + 32, v + 32);
+      double ph = (double)p.b_coor2;  // 64-term dot in fp64: phi multiplies x_rel, which reaches 10^2..10^3 A
+#pragma unroll
+      for (int c = 0; c < 64; ++c) ph = fma((double)lrelu(v[c] + cst.b3[c], p.leaky_slope), (double)cst.w4[c], ph);  // :153-159
+      W.xm[r * 3 + 0] = rx * ph;  // x_rel * phi :264
+      W.xm[r * 3 + 1] = ry * ph;
+      W.xm[r * 3 + 2] = rz * ph;
+    }
+    tc_fence_before();
+    wg_barrier(wg);
+    for (int o = r; o < nn * 3; o += 128) {  // :274-277, 286-292
+      int nd = o / 3, comp = o - nd * 3;
+      int rs = W.rp[buf][nd] - e0, re = W.rp[buf][nd + 1] - e0;
+      double sum = 0.0;
+      for (int rr = rs; rr < re; ++rr) sum += W.xm[rr * 3 + comp];
+      int deg = re - rs;
+      double upd = deg > 0 ? sum / (double)deg : 0.0;
+      long gi = (long)(n0 + nd) * 3 + comp;
+      double eta = (double)p.x_connection_init;
+      x_out[gi] = eta * x_orig[gi] + (1.0 - eta) * x_in[gi] + upd;
+    }
+    e0 = e0n; ne = nen; off_l = off_ln; n_l = n_ln; off_r = off_rn; buf ^= 1;
+  }
+  cp_async_wait<0>();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base), "r"(512));
+}
+
+}  // namespace eqd
+
+extern "C" int eqd_edge_stage(const eqd_graph* g, const eqd_layer_params* p, const float* proj, const double* x_in,
+                              const double* x_orig, float* aggr, double* x_out, int32_t* status, void* stream) {
+  if (!g || !p || !proj || !x_in || !x_orig || !aggr || !x_out || !status) return EQD_ERR_BAD_ARG;
+  if (!p->w_edge_tc || !p->edge_consts_host) return EQD_ERR_BAD_ARG;
+  if (g->max_in_degree < 1 || g->max_in_degree > EQD_TM) return EQD_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(g->he_lig) | reinterpret_cast<uintptr_t>(g->he_rec) |
+       reinterpret_cast<uintptr_t>(p->w_edge_tc)) & 15)
+    return EQD_ERR_BAD_ARG;  // bulk copies need 16-byte aligned bases
+  if (g->n_nodes <= 0) return EQD_OK;
+  int tn = EQD_TM / g->max_in_degree;
+  if (tn > TC_MAX_TN) tn = TC_MAX_TN;
+  int ntiles = (g->n_nodes + tn - 1) / tn;
+  eqd::EdgeConsts cst;
+  memcpy(&cst, p->edge_consts_host, sizeof(cst));
+  size_t smem = sizeof(eqd::TcSmem) + 128;
+  cudaFuncSetAttribute(eqd::edge_stage_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int grid = (ntiles + 1) / 2;
+  if (grid > 148) grid = 148;
+  eqd::edge_stage_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(*g, *p, cst, proj, x_in, x_orig, aggr, x_out,
+                                                                             status, tn);
+  EQD_CUDA_LAUNCH_CHECK();
+  return EQD_OK;
+}

@@ -21,6 +21,21 @@ def _dev_f32(t, device):
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
+def umma_bf16x3(w: torch.Tensor) -> torch.Tensor:
+    """[N][K] fp32 weight (nn.Linear layout, K % 8 == 0) -> 3 bf16 splits (w ~ w0+w1+w2, round to nearest), each in
+    the UMMA canonical K-major no-swizzle layout: element (n,k) at (k/8)*N*16 + (n/8)*128 + (n%8)*16 + (k%8)*2 bytes.
+    Returns a flat bf16 tensor [3 * N * K]."""
+    n, k = w.shape
+    assert n % 8 == 0 and k % 8 == 0
+    parts, r = [], w.to(torch.float32)
+    for _ in range(3):
+        b = r.to(torch.bfloat16)
+        parts.append(b)
+        r = r - b.to(torch.float32)
+    out = [b.reshape(n // 8, 8, k // 8, 8).permute(2, 0, 1, 3).contiguous().reshape(-1) for b in parts]
+    return torch.cat(out)
+
+
 class PackedLayer:
     """One IEGMN_Layer's parameters repacked k-major for the kernels (see eqd_layer_params)."""
 
@@ -57,6 +72,13 @@ class PackedLayer:
         w_node2 = z(dhp, 64)
         w_node2[:dh] = w6.t()
         self.dh, self.dhp = dh, dhp
+        w1e = z(64, 48)
+        w1e[:, :n_e] = w1[:, 2 * dh:]
+        w_edge_tc = torch.cat([umma_bf16x3(w1e), umma_bf16x3(f('edge_mlp.4.weight')),
+                               umma_bf16x3(f('coors_mlp.0.weight'))]).contiguous()
+        assert w_edge_tc.numel() * 2 == 67584
+        self.edge_consts_host = torch.stack([f('edge_mlp.3.weight'), f('edge_mlp.3.bias'), f('edge_mlp.4.bias'),
+                                             f('coors_mlp.0.bias'), f('coors_mlp.4.weight').reshape(-1)]).cpu().contiguous()
         self.t = {
             'w_proj': w_proj, 'b_proj': b_proj, 'w_edge1': w_edge1,
             'edge_ln_g': f('edge_mlp.3.weight'), 'edge_ln_b': f('edge_mlp.3.bias'),
@@ -65,12 +87,13 @@ class PackedLayer:
             'w_coor2': f('coors_mlp.4.weight').reshape(-1).contiguous(),
             'w_node1': w_node1, 'b_node1': pad(b5),
             'node_ln_g': pad(f('node_mlp.3.weight')), 'node_ln_b': pad(f('node_mlp.3.bias')),
-            'w_node2': w_node2, 'b_node2': b6,
+            'w_node2': w_node2, 'b_node2': b6, 'w_edge_tc': w_edge_tc,
         }
         s = nat.EqdLayerParams()
         s.dh, s.dhp = dh, dhp
         for k, v in self.t.items():
             setattr(s, k, v.data_ptr())
+        s.edge_consts_host = self.edge_consts_host.data_ptr()
         s.b_coor2 = float(sd['coors_mlp.4.bias'].detach().reshape(-1)[0].item())
         s.skip_weight_h, s.x_connection_init, s.leaky_slope = skip_weight_h, x_connection_init, leaky_slope
         self.struct = s

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define EQD_ABI_VERSION 1
+#define EQD_ABI_VERSION 2
 
 #define EQD_EDGE_FEATS 27     /* input_edge_feats_dim, protein_utils.py:71-86 + :373-389 */
 #define EQD_N_RBF 15          /* all_sigmas_dist = 1.5**s, rigid_docking_model.py:116 */
@@ -97,6 +97,15 @@ typedef struct eqd_layer_params {
   const float* b_coor1;       /* [64] */
   const float* w_coor2;       /* [64] coors_mlp.4.weight */
   float b_coor2;              /* coors_mlp.4.bias */
+  /* tensor-core edge stage (tcgen05): the three edge-side weight matrices, each split into 3 bf16 terms
+   * (w ~ w0+w1+w2, round-to-nearest) and stored in the UMMA canonical K-major no-swizzle layout
+   *   element (n,k) of split s at  base + s*split_bytes + (k/8)*1024 + (n/8)*128 + (n%8)*16 + (k%8)*2
+   * GEMM1 = edge_mlp.0.weight[:, 2dh:] (K 42 -> 48, base 0, split 6144 B), GEMM2 = edge_mlp.4.weight
+   * (base 18432, split 8192 B), GEMM3 = coors_mlp.0.weight (base 43008, split 8192 B); 67584 B, 16B-aligned. */
+  const void* w_edge_tc;
+  /* HOST pointer to [5][64] floats: edge_ln_g, edge_ln_b, b_edge2, b_coor1, w_coor2 (copied into the kernel's
+   * constant parameter space at launch). */
+  const float* edge_consts_host;
   const float* w_node1;       /* [dhp+64+dhp+72][dhp] node_mlp.0.weight^T, row blocks [h | aggr_msg | mu | h0] */
   const float* b_node1;       /* [dhp] */
   const float* node_ln_g;     /* [dhp] node_mlp.3.weight (pad 0) */
@@ -137,10 +146,17 @@ int eqd_project(const eqd_graph* g, const eqd_layer_params* p, const float* h, i
 
 /* Edge stage of IEGMN_Layer.forward (:204-237, 263-292): RBF, edge MLP, coordinate MLP, mean
  * aggregation at the destination, coordinate update.
- *   aggr[n][64] = mean_e msg_e ;  x_out[n] = eta*x_orig[n] + (1-eta)*x_in[n] + mean_e x_rel*phi  */
+ *   aggr[n][64] = mean_e msg_e ;  x_out[n] = eta*x_orig[n] + (1-eta)*x_in[n] + mean_e x_rel*phi
+ * Runs on tcgen05 tensor cores (bf16x3 operand split, fp32 accumulation in TMEM).  he_lig / he_rec must be
+ * 16-byte aligned and readable up to the next 16-byte boundary past their end (TMA bulk copies).          */
 int eqd_edge_stage(const eqd_graph* g, const eqd_layer_params* p, const float* proj,
                    const double* x_in, const double* x_orig, float* aggr, double* x_out,
                    int32_t* status /* [n_pairs+1] */, void* stream);
+
+/* Same contract on the fp32 CUDA cores (FFMA); kept as the validation twin of the tensor-core kernel. */
+int eqd_edge_stage_ffma(const eqd_graph* g, const eqd_layer_params* p, const float* proj,
+                        const double* x_in, const double* x_orig, float* aggr, double* x_out,
+                        int32_t* status /* [n_pairs+1] */, void* stream);
 
 /* Node stage (:244-256, 319-349): segmented cross attention mu = softmax(q k^T) v over the partner
  * protein, node MLP + LayerNorm + skip -> h_out[n][64]; if p_next != NULL also the next layer's

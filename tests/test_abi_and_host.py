@@ -43,7 +43,8 @@ def test_struct_layouts_are_natural_c_layouts():
     assert ctypes.sizeof(nat.EqdGraph) == 24 + 6 * 8 + 8 + 8
     assert nat.EqdGraph.seg_ptr.offset == 24 and nat.EqdGraph.node_tiles.offset == 80
     assert nat.EqdLayerParams.w_proj.offset == 8 and nat.EqdLayerParams.b_coor2.offset == 8 + 10 * 8
-    assert nat.EqdLayerParams.w_node1.offset == 8 + 10 * 8 + 8
+    assert nat.EqdLayerParams.w_edge_tc.offset == 96 and nat.EqdLayerParams.edge_consts_host.offset == 104
+    assert nat.EqdLayerParams.w_node1.offset == 112
     assert ctypes.sizeof(nat.EqdHeadParams) == 4 * 8 + 8
 
 
