@@ -17,8 +17,7 @@
 #include "common.cuh"
 
 namespace eqd {
-
-#define TC_THREADS 256
+#define TC_THREADS 512
 #define TC_MAX_TN 32          // destination nodes per tile (Pdst staging rows)
 #define TC_LD 68              // fp32 row stride of the staging / msg tile
 #define TC_W_BYTES 67584      // 3 splits x (6144 + 8192 + 8192)
@@ -33,6 +32,8 @@ struct TcWgSmem {                         // per warpgroup
   float pdst[TC_MAX_TN * TC_LD];          // Pdst rows of the tile's destination nodes
   float he[TC_HE_STAGE_FLOATS];           // raw he rows of the tile (bulk-copied, 16B-aligned chunks)
   double xm[EQD_TM * 3];                  // x_rel * phi per edge
+  double xs[EQD_TM * 6];                  // x[src], x[dst] of the tile's edges (prefetched one tile ahead)
+  double red[EQD_TM * 4];                 // per-row partial reductions exchanged between the two column halves
   int src[2][EQD_TM];
   int dst[2][EQD_TM];
   int rp[2][TC_MAX_TN + 4];
@@ -73,10 +74,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src));
+}
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src));
 }
-__device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+__device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 256;" ::"r"(wg + 1) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -106,6 +110,11 @@ __device__ __forceinline__ void issue_gemm(unsigned d_tmem, unsigned a_base, uns
       accum = 1;
     }
 }
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -134,8 +143,7 @@ __device__ __forceinline__ void tmem_st8(unsigned taddr, const unsigned* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
                "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, float* v) {
-  unsigned r[32];
+__device__ __forceinline__ void tmem_ld32_nowait(unsigned taddr, unsigned (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
       "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -144,34 +152,55 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float* v) {
         "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
+}
+// this thread's 64-column accumulator row: two TMEM loads in flight, one wait
+__device__ __forceinline__ void tmem_ld64(unsigned taddr, float (&v)[64]) {
+  unsigned a[32], b[32];
+  tmem_ld32_nowait(taddr, a);
+  tmem_ld32_nowait(taddr + 32, b);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-// 64 fp32 values of this thread's row -> bf16x3 -> TMEM A region (3 splits x 32 columns)
-__device__ __forceinline__ void store_row_split3(unsigned a_taddr, const float (&v)[64]) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    unsigned p0[16], p1[16], p2[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) split3_pair(v[h * 32 + 2 * c], v[h * 32 + 2 * c + 1], p0[c], p1[c], p2[c]);
-    tmem_st16(a_taddr + h * 16, p0);
-    tmem_st16(a_taddr + 32 + h * 16, p1);
-    tmem_st16(a_taddr + 64 + h * 16, p2);
+  for (int i = 0; i < 32; ++i) {
+    v[i] = __uint_as_float(a[i]);
+    v[32 + i] = __uint_as_float(b[i]);
   }
+}
+// 32 fp32 values (this thread's half of its row) -> bf16x3 -> TMEM: split s lands at a_taddr + 32*s, 16 columns
+__device__ __forceinline__ void store_half_split3(unsigned a_taddr, const float (&v)[32]) {
+  unsigned p0[16], p1[16], p2[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) split3_pair(v[2 * c], v[2 * c + 1], p0[c], p1[c], p2[c]);
+  tmem_st16(a_taddr, p0);
+  tmem_st16(a_taddr + 32, p1);
+  tmem_st16(a_taddr + 64, p2);
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_st4(unsigned taddr, const unsigned* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32f(unsigned taddr, float (&v)[32]) {
+  unsigned a[32];
+  tmem_ld32_nowait(taddr, a);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(a[i]);
+}
 
+// 512 threads = 2 tile groups x 256; in a group, thread (r = q & 127, half = q >> 7) owns columns
+// [32*half, 32*half+32) of edge row r (TMEM lane r): two threads per row keep the per-thread register
+// footprint <= 128 so that 16 warps (4 per scheduler) hide each other's latencies.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ EdgeConsts cst,
                      const float* __restrict__ proj, const double* __restrict__ x_in, const double* __restrict__ x_orig,
                      float* __restrict__ aggr, double* __restrict__ x_out, int* __restrict__ status, int tn) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
-  const int tid = threadIdx.x, wg = tid >> 7, r = tid & 127, warp = tid >> 5;
+  const int tid = threadIdx.x, wg = tid >> 8, q = tid & 255, half = q >> 7, r = q & 127, warp = tid >> 5;
   TcWgSmem& W = S.wg[wg];
   const int pw = 128 + 3 * p.dhp;
   const int ntiles = (g.n_nodes + tn - 1) / tn;
+  const float slope = p.leaky_slope;
 
   // ---- one-time setup: TMEM, barriers, weights (one TMA bulk copy) -------------------------------
   if (warp == 0) {
@@ -191,15 +220,21 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const unsigned tmem = S.tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)wg * 256;  // my lane quarter, my column half
-  const unsigned d_col = tmem;            // D: 64 columns
-  const unsigned a_col = tmem + 64;       // A: 3 splits x 32 columns
-  const unsigned tmem_wg = S.tmem_base + (unsigned)wg * 256;  // lane 0 address for the MMA issuer
+  // warp-uniform copies for the MMA issue path: operands the compiler can prove uniform go straight to uniform
+  // registers (UTCHMMA takes UR operands); anything else costs a per-MMA waterfall loop (ELECT / R2UR / BRA.U.ANY)
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int wg_u = warp_u >> 3;
+  const bool issuer_warp = (warp_u & 7) == 0;
+  const unsigned tmem_base_u = __shfl_sync(0xffffffffu, S.tmem_base, 0);
+  const unsigned tmem_wg = tmem_base_u + (unsigned)wg_u * 256;                   // lane 0 (MMA issuer's view)
+  const unsigned tmem = tmem_wg + ((unsigned)((warp & 3) * 32) << 16);           // my lane quarter
+  const unsigned d_col = tmem + half * 32;                                         // my half of D (64 columns)
+  const unsigned a_col = tmem + 64;                                                // A: 3 splits x 32 columns
   mbar_wait(&S.w_bar, 0);
   unsigned mma_phase = 0, he_phase = 0;
   const unsigned w_saddr = smem_u32(S.w);
 
-  // Prefetch of a tile's indices + he rows.  Returns e0 / ne of that tile.
+  // Prefetch of a tile's indices + he rows (issued by the half-0 threads).
   auto prefetch = [&](int tile, int buf, int& e0_out, int& ne_out, int& off_l, int& n_l, int& off_r) {
     const int n0 = tile * tn, nn = min(tn, g.n_nodes - n0);
     const int e0 = __ldg(g.row_ptr + n0), e1 = __ldg(g.row_ptr + n0 + nn);
@@ -209,15 +244,16 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     off_l = off_r = 0;
     n_l = 0;
     if (ne <= EQD_TM) {
-      if (r < ne) {
-        cp_async4(&W.src[buf][r], g.col_src + e0 + r);
-        cp_async4(&W.dst[buf][r], g.edge_dst + e0 + r);
+      if (half == 0) {
+        if (r < ne) {
+          cp_async4(&W.src[buf][r], g.col_src + e0 + r);
+          cp_async4(&W.dst[buf][r], g.edge_dst + e0 + r);
+        }
+        if (r <= nn) cp_async4(&W.rp[buf][r], g.row_ptr + n0 + r);
       }
-      if (r <= nn) cp_async4(&W.rp[buf][r], g.row_ptr + n0 + r);
       // he rows: [e0, e1) split at the ligand/receptor array boundary; 16-byte aligned bulk copies
       const int el0 = min(e0, g.n_lig_edges), el1 = min(e1, g.n_lig_edges);
       n_l = el1 - el0;
-      unsigned bytes = 0;
       long sl = 0, sr = 0;
       unsigned bl = 0, br = 0;
       if (n_l > 0) {
@@ -227,20 +263,28 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
         off_l = (int)((b0 - sl) >> 2);
       }
       const int nr = ne - n_l;
-      unsigned dst_r_off = (bl + 15u) & ~15u;  // receptor part lands after the ligand part
+      const unsigned dst_r_off = bl;  // receptor part lands after the ligand part (bl is a multiple of 16)
       if (nr > 0) {
         long b0 = (long)(e0 + n_l - g.n_lig_edges) * (EQD_EDGE_FEATS * 4), b1 = (long)(e1 - g.n_lig_edges) * (EQD_EDGE_FEATS * 4);
         sr = b0 & ~15L;
         br = (unsigned)(((b1 + 15) & ~15L) - sr);
         off_r = (int)(dst_r_off >> 2) + (int)((b0 - sr) >> 2);
       }
-      bytes = bl + br;
-      if (r == 0) {
-        mbar_expect_tx(&S.he_bar[wg], bytes);
+      if (q == 0) {
+        mbar_expect_tx(&S.he_bar[wg], bl + br);
         if (bl) bulk_g2s(W.he, reinterpret_cast<const unsigned char*>(g.he_lig) + sl, bl, &S.he_bar[wg]);
         if (br) bulk_g2s(reinterpret_cast<unsigned char*>(W.he) + dst_r_off, reinterpret_cast<const unsigned char*>(g.he_rec) + sr, br,
                          &S.he_bar[wg]);
       }
+    }
+    cp_async_commit();
+  };
+  // Coordinates of a tile's edge endpoints -> smem (needs that tile's indices to have landed).
+  auto prefetch_x = [&](int b, int ne_t) {
+    if (r < ne_t && ne_t <= EQD_TM) {
+      const double* xp = x_in + (long)(half == 0 ? W.src[b][r] : W.dst[b][r]) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) cp_async8(&W.xs[r * 6 + half * 3 + c], xp + c);
     }
     cp_async_commit();
   };
@@ -249,80 +293,94 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
   const int tstride = gridDim.x * 2;
   int buf = 0;
   int e0 = 0, ne = 0, off_l = 0, n_l = 0, off_r = 0;
-  if (tile < ntiles) prefetch(tile, buf, e0, ne, off_l, n_l, off_r);
+  if (tile < ntiles) {
+    prefetch(tile, buf, e0, ne, off_l, n_l, off_r);
+    cp_async_wait<0>();
+    wg_barrier(wg);
+    prefetch_x(buf, ne);
+  }
 
   for (; tile < ntiles; tile += tstride) {
     const int n0 = tile * tn, nn = min(tn, g.n_nodes - n0);
     const bool has_next = tile + tstride < ntiles;
     int e0n = 0, nen = 0, off_ln = 0, n_ln = 0, off_rn = 0;
-    if (ne > EQD_TM) {  // in-degree bound violated: flag, skip (uniform per warpgroup)
-      if (r == 0) atomicOr(status + g.n_pairs, EQD_STATUS_DEGREE_OVERFLOW);
+    if (ne > EQD_TM) {  // in-degree bound violated: flag, skip (uniform per tile group)
+      if (q == 0) atomicOr(status + g.n_pairs, EQD_STATUS_DEGREE_OVERFLOW);
       cp_async_wait<0>();
       wg_barrier(wg);
-      if (has_next) prefetch(tile + tstride, buf ^ 1, e0n, nen, off_ln, n_ln, off_rn);
+      if (has_next) {
+        prefetch(tile + tstride, buf ^ 1, e0n, nen, off_ln, n_ln, off_rn);
+        cp_async_wait<0>();
+        wg_barrier(wg);
+        prefetch_x(buf ^ 1, nen);
+      }
       e0 = e0n; ne = nen; off_l = off_ln; n_l = n_ln; off_r = off_rn; buf ^= 1;
       continue;
     }
-    // ---- S0/S1: indices ready; gathers; geometry; [he|rbf] -> TMEM ---------------------------------
+    // ---- S0/S1: indices + coordinates ready; gathers; geometry; [he|rbf] -> TMEM -----------------------
     cp_async_wait<0>();
     wg_barrier(wg);
     const bool valid = r < ne;
-    const int sn = valid ? W.src[buf][r] : 0, dn = valid ? W.dst[buf][r] : 0;
+    const int dn = valid ? W.dst[buf][r] : 0;
     // gathers of the node projections into smem (coalesced 16B chunks, 16 lanes per row)
-    for (int idx = r; idx < EQD_TM * 16; idx += 128) {
+#pragma unroll
+    for (int idx = q; idx < EQD_TM * 16; idx += 256) {
       int row = idx >> 4, c4 = idx & 15;
       bool ok = row < ne;
       int s_row = ok ? W.src[buf][row] : 0;
       cp_async16(&W.stage[row * TC_LD + c4 * 4], proj + (long)s_row * pw + c4 * 4, ok);
     }
-    for (int idx = r; idx < nn * 16; idx += 128) {
+    for (int idx = q; idx < nn * 16; idx += 256) {
       int row = idx >> 4, c4 = idx & 15;
       cp_async16(&W.pdst[row * TC_LD + c4 * 4], proj + (long)(n0 + row) * pw + 64 + c4 * 4, true);
     }
     cp_async_commit();
     double rx = 0.0, ry = 0.0, rz = 0.0;
     {
-      float a1v[48];
-      if (valid) {
-        rx = x_in[(long)sn * 3 + 0] - x_in[(long)dn * 3 + 0];  // u_sub_v :204-205
-        ry = x_in[(long)sn * 3 + 1] - x_in[(long)dn * 3 + 1];
-        rz = x_in[(long)sn * 3 + 2] - x_in[(long)dn * 3 + 2];
-      }
+      float a1v[24];  // half 0: he[0..23];  half 1: he[24..26], 15 RBFs, 6 zeros
       mbar_wait(&S.he_bar[wg], he_phase);
       he_phase ^= 1;
       const float* hrow = W.he + (r < n_l ? off_l + r * EQD_EDGE_FEATS : off_r + (r - n_l) * EQD_EDGE_FEATS);
+      if (half == 0) {
 #pragma unroll
-      for (int k = 0; k < EQD_EDGE_FEATS; ++k) a1v[k] = valid ? hrow[k] : 0.f;
-      const float nd2 = -(float)(rx * rx + ry * ry + rz * rz);  // :208-209
-      // exp(-d^2 / 1.5^q) :210 -- correctly rounded reciprocals of sigma (1.5^q is exact in fp32)
-      constexpr double kS[EQD_N_RBF] = {1.0, 1.5, 2.25, 3.375, 5.0625, 7.59375, 11.390625, 17.0859375, 25.62890625,
-                                        38.443359375, 57.6650390625, 86.49755859375, 129.746337890625,
-                                        194.6195068359375, 291.92926025390625};
+        for (int k = 0; k < 24; ++k) a1v[k] = valid ? hrow[k] : 0.f;
+      } else {
+        if (valid) {  // u_sub_v :204-205
+          rx = W.xs[r * 6 + 0] - W.xs[r * 6 + 3];
+          ry = W.xs[r * 6 + 1] - W.xs[r * 6 + 4];
+          rz = W.xs[r * 6 + 2] - W.xs[r * 6 + 5];
+        }
 #pragma unroll
-      for (int q = 0; q < EQD_N_RBF; ++q) a1v[EQD_EDGE_FEATS + q] = valid ? expf(nd2 * (float)(1.0 / kS[q])) : 0.f;
+        for (int k = 0; k < 3; ++k) a1v[k] = valid ? hrow[24 + k] : 0.f;
+        const float nd2 = -(float)(rx * rx + ry * ry + rz * rz);  // :208-209
+        // exp(-d^2 / 1.5^q) :210 -- correctly rounded reciprocals of sigma (1.5^q is exact in fp32)
+        constexpr double kS[EQD_N_RBF] = {1.0, 1.5, 2.25, 3.375, 5.0625, 7.59375, 11.390625, 17.0859375, 25.62890625,
+                                          38.443359375, 57.6650390625, 86.49755859375, 129.746337890625,
+                                          194.6195068359375, 291.92926025390625};
 #pragma unroll
-      for (int k = 42; k < 48; ++k) a1v[k] = 0.f;
-      unsigned p0[24], p1[24], p2[24];
+        for (int j = 0; j < EQD_N_RBF; ++j) a1v[3 + j] = valid ? expf(nd2 * (float)(1.0 / kS[j])) : 0.f;
 #pragma unroll
-      for (int c = 0; c < 24; ++c) split3_pair(a1v[2 * c], a1v[2 * c + 1], p0[c], p1[c], p2[c]);
-      unsigned v16[16];
-#define EQD_ST24(base, arr)                      \
-  _Pragma("unroll") for (int c = 0; c < 16; ++c) v16[c] = arr[c]; \
-  tmem_st16(base, v16);                          \
-  tmem_st8(base + 16, arr + 16);
-      EQD_ST24(a_col, p0)
-      EQD_ST24(a_col + 32, p1)
-      EQD_ST24(a_col + 64, p2)
-#undef EQD_ST24
+        for (int k = 18; k < 24; ++k) a1v[k] = 0.f;
+      }
+      unsigned p0[12], p1[12], p2[12];
+#pragma unroll
+      for (int c = 0; c < 12; ++c) split3_pair(a1v[2 * c], a1v[2 * c + 1], p0[c], p1[c], p2[c]);
+      const unsigned ab = a_col + half * 12;
+      tmem_st8(ab, p0);      tmem_st4(ab + 8, p0 + 8);
+      tmem_st8(ab + 32, p1); tmem_st4(ab + 40, p1 + 8);
+      tmem_st8(ab + 64, p2); tmem_st4(ab + 72, p2 + 8);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     wg_barrier(wg);
     // ---- GEMM1: [he|rbf] (K=48) x W1e ---------------------------------------------------------------
-    if (r == 0) {
+    if (issuer_warp) {
       tc_fence_after();
-      issue_gemm(tmem_wg, tmem_wg + 64, 32, w_saddr, TC_W1_SPLIT, 3);
-      umma_commit(&S.mma_bar[wg]);
+      if (elect_one()) {
+        issue_gemm(tmem_wg, tmem_wg + 64, 32, w_saddr, TC_W1_SPLIT, 3);
+        umma_commit(&S.mma_bar[wg_u]);
+      }
+      __syncwarp();
     }
     // he staging and the other index buffer are free now: prefetch the next tile behind the MMAs
     if (has_next) prefetch(tile + tstride, buf ^ 1, e0n, nen, off_ln, n_ln, off_rn);
@@ -331,90 +389,121 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     tc_fence_after();
     // ---- epilogue 1: + Psrc[src] + Pdst[dst], LeakyReLU, LayerNorm -> bf16x3 -> TMEM ----------------
     {
-      float v[64];
-      tmem_ld32(d_col, v);
-      tmem_ld32(d_col + 32, v + 32);
+      float v[32];
+      tmem_ld32f(d_col, v);
       if (has_next) cp_async_wait<1>(); else cp_async_wait<0>();  // gathers landed (the newest group is the prefetch)
       wg_barrier(wg);
       const int dloc = valid ? dn - n0 : 0;
-      const float4* ps = reinterpret_cast<const float4*>(&W.stage[r * TC_LD]);
-      const float4* pd = reinterpret_cast<const float4*>(&W.pdst[dloc * TC_LD]);
-      float sum = 0.f;
+      const float4* ps = reinterpret_cast<const float4*>(&W.stage[r * TC_LD + half * 32]);
+      const float4* pd = reinterpret_cast<const float4*>(&W.pdst[dloc * TC_LD + half * 32]);
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c4 = 0; c4 < 16; ++c4) {
+      for (int c4 = 0; c4 < 8; ++c4) {
         float4 a = ps[c4], b = pd[c4];
-        float t0 = lrelu(v[c4 * 4 + 0] + a.x + b.x, p.leaky_slope), t1 = lrelu(v[c4 * 4 + 1] + a.y + b.y, p.leaky_slope);
-        float t2 = lrelu(v[c4 * 4 + 2] + a.z + b.z, p.leaky_slope), t3 = lrelu(v[c4 * 4 + 3] + a.w + b.w, p.leaky_slope);
+        float t0 = lrelu(v[c4 * 4 + 0] + a.x + b.x, slope), t1 = lrelu(v[c4 * 4 + 1] + a.y + b.y, slope);
+        float t2 = lrelu(v[c4 * 4 + 2] + a.z + b.z, slope), t3 = lrelu(v[c4 * 4 + 3] + a.w + b.w, slope);
         v[c4 * 4 + 0] = t0; v[c4 * 4 + 1] = t1; v[c4 * 4 + 2] = t2; v[c4 * 4 + 3] = t3;
-        sum += (t0 + t1) + (t2 + t3);
+        s4[0] += t0; s4[1] += t1; s4[2] += t2; s4[3] += t3;
       }
-      const float mean = sum * (1.f / 64.f);
-      float q = 0.f;
+      // LayerNorm statistics: two-pass over this half (mean_h, M2_h), then the exact pairwise combination
+      //   mean = (m0+m1)/2,  M2 = M2_0 + M2_1 + (m0-m1)^2 * 16      (Chan et al.)
+      const float mh = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.f / 32.f);
+      float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        float d = v[c] - mean;
-        q = fmaf(d, d, q);
+      for (int c = 0; c < 32; ++c) {
+        float d = v[c] - mh;
+        q4[c & 3] = fmaf(d, d, q4[c & 3]);
       }
-      const float rstd = 1.f / sqrtf(q * (1.f / 64.f) + 1e-5f);
+      float* redf = reinterpret_cast<float*>(W.red);
+      redf[(r * 2 + half) * 2 + 0] = mh;
+      redf[(r * 2 + half) * 2 + 1] = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+      wg_barrier(wg);
+      const float m0 = redf[r * 4 + 0], m1 = redf[r * 4 + 2];
+      const float mean = 0.5f * (m0 + m1);
+      const float dm = m0 - m1;
+      const float var = (redf[r * 4 + 1] + redf[r * 4 + 3] + dm * dm * 16.f) * (1.f / 64.f);
+      const float rstd = 1.f / sqrtf(var + 1e-5f);
 #pragma unroll
-      for (int c = 0; c < 64; ++c) v[c] = (v[c] - mean) * rstd * cst.ln_g[c] + cst.ln_b[c];
-      store_row_split3(a_col, v);
+      for (int c = 0; c < 32; ++c) v[c] = (v[c] - mean) * rstd * cst.ln_g[half * 32 + c] + cst.ln_b[half * 32 + c];
+      store_half_split3(a_col + half * 16, v);
     }
     tc_fence_before();
     wg_barrier(wg);  // A operand complete; everyone is done with the Psrc staging (it becomes the msg tile)
     // ---- GEMM2: edge_mlp.4 -> msg ---------------------------------------------------------------------
-    if (r == 0) {
+    if (issuer_warp) {
       tc_fence_after();
-      issue_gemm(tmem_wg, tmem_wg + 64, 32, w_saddr + TC_W2_BASE, TC_W23_SPLIT, 4);
-      umma_commit(&S.mma_bar[wg]);
+      if (elect_one()) {
+        issue_gemm(tmem_wg, tmem_wg + 64, 32, w_saddr + TC_W2_BASE, TC_W23_SPLIT, 4);
+        umma_commit(&S.mma_bar[wg_u]);
+      }
+      __syncwarp();
     }
     mbar_wait(&S.mma_bar[wg], mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
     {
-      float v[64];
-      tmem_ld32(d_col, v);
-      tmem_ld32(d_col + 32, v + 32);
+      float v[32];
+      tmem_ld32f(d_col, v);
 #pragma unroll
-      for (int c = 0; c < 64; ++c) v[c] += cst.b2[c];
-      float4* ms = reinterpret_cast<float4*>(&W.stage[r * TC_LD]);
+      for (int c = 0; c < 32; ++c) v[c] += cst.b2[half * 32 + c];
+      float4* ms = reinterpret_cast<float4*>(&W.stage[r * TC_LD + half * 32]);
 #pragma unroll
-      for (int c4 = 0; c4 < 16; ++c4) ms[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
-      store_row_split3(a_col, v);
+      for (int c4 = 0; c4 < 8; ++c4) ms[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+      store_half_split3(a_col + half * 16, v);
+    }
+    cp_async_wait<0>();  // next tile's indices have landed (issued behind GEMM1)
+    tc_fence_before();
+    wg_barrier(wg);
+    if (has_next) prefetch_x(buf ^ 1, nen);  // its x[src], x[dst]: xs of this tile was consumed in S1
+    // ---- GEMM3: coors_mlp.0 ; mean aggregation of msg overlaps the MMAs ---------------------------------
+    if (issuer_warp) {
+      tc_fence_after();
+      if (elect_one()) {
+        issue_gemm(tmem_wg, tmem_wg + 64, 32, w_saddr + TC_W3_BASE, TC_W23_SPLIT, 4);
+        umma_commit(&S.mma_bar[wg_u]);
+      }
+      __syncwarp();
+    }
+    for (int o = q; o < nn * 64; o += 256) {  // :280-283
+      const int nd = o >> 6, c = o & 63;
+      const int rs = W.rp[buf][nd] - e0, re = W.rp[buf][nd + 1] - e0;
+      const float* col = W.stage + c;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int rr = rs;
+      for (; rr + 4 <= re; rr += 4) {  // 4 independent loads in flight
+        s0 += col[rr * TC_LD];
+        s1 += col[(rr + 1) * TC_LD];
+        s2 += col[(rr + 2) * TC_LD];
+        s3 += col[(rr + 3) * TC_LD];
+      }
+      if (rr < re) s0 += col[rr * TC_LD];
+      if (rr + 1 < re) s1 += col[(rr + 1) * TC_LD];
+      if (rr + 2 < re) s2 += col[(rr + 2) * TC_LD];
+      const int deg = re - rs;
+      aggr[(long)(n0 + nd) * 64 + c] = deg > 0 ? ((s0 + s1) + (s2 + s3)) / (float)deg : 0.f;
+    }
+    mbar_wait(&S.mma_bar[wg], mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+    {
+      float v[32];
+      tmem_ld32f(d_col, v);
+      float ph4[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent chains; the two halves are combined in fp64
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        ph4[c & 3] = fmaf(lrelu(v[c] + cst.b3[half * 32 + c], slope), cst.w4[half * 32 + c], ph4[c & 3]);  // :153-159
+      W.red[r * 2 + half] = ((double)ph4[0] + (double)ph4[1]) + ((double)ph4[2] + (double)ph4[3]);
     }
     tc_fence_before();
     wg_barrier(wg);
-    // ---- GEMM3: coors_mlp.0 ; mean aggregation of msg overlaps the MMAs ---------------------------------
-    if (r == 0) {
-      tc_fence_after();
-      issue_gemm(tmem_wg, tmem_wg + 64, 32, w_saddr + TC_W3_BASE, TC_W23_SPLIT, 4);
-      umma_commit(&S.mma_bar[wg]);
-    }
-    for (int o = r; o < nn * 64; o += 128) {  // :280-283
-      int nd = o >> 6, c = o & 63;
-      int rs = W.rp[buf][nd] - e0, re = W.rp[buf][nd + 1] - e0;
-      float sum = 0.f;
-      for (int rr = rs; rr < re; ++rr) sum += W.stage[rr * TC_LD + c];
-      int deg = re - rs;
-      aggr[(long)(n0 + nd) * 64 + c] = deg > 0 ? sum / (float)deg : 0.f;
-    }
-    mbar_wait(&S.mma_bar[wg], mma_phase);
-    mma_phase ^= 1;
-    tc_fence_after();
-    {
-      float v[64];
-      tmem_ld32(d_col, v);
-      tmem_ld32(d_col + 32, v + 32);
-      double ph = (double)p.b_coor2;  // 64-term dot in fp64: phi multiplies x_rel, which reaches 10^2..10^3 A
-#pragma unroll
-      for (int c = 0; c < 64; ++c) ph = fma((double)lrelu(v[c] + cst.b3[c], p.leaky_slope), (double)cst.w4[c], ph);  // :153-159
+    if (half == 1) {
+      const double ph = W.red[r * 2] + W.red[r * 2 + 1] + (double)p.b_coor2;
       W.xm[r * 3 + 0] = rx * ph;  // x_rel * phi :264
       W.xm[r * 3 + 1] = ry * ph;
       W.xm[r * 3 + 2] = rz * ph;
     }
-    tc_fence_before();
     wg_barrier(wg);
-    for (int o = r; o < nn * 3; o += 128) {  // :274-277, 286-292
+    for (int o = q; o < nn * 3; o += 256) {  // :274-277, 286-292
       int nd = o / 3, comp = o - nd * 3;
       int rs = W.rp[buf][nd] - e0, re = W.rp[buf][nd + 1] - e0;
       double sum = 0.0;
