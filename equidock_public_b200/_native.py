@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libeqd_iegmn.so')
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 EDGE_FEATS, N_RBF, HID, H0, H0_PAD, N_RES_TYPES, HEADS, TILE_ROWS = 27, 15, 64, 69, 72, 21, 50, 128
 STATUS_SVD_DEGENERATE, STATUS_NAN, STATUS_DEGREE_OVERFLOW = 1, 2, 4
 
@@ -31,6 +31,7 @@ class EqdLayerParams(C.Structure):
                 ('w_proj', _vp), ('b_proj', _vp), ('w_edge1', _vp), ('edge_ln_g', _vp), ('edge_ln_b', _vp),
                 ('w_edge2', _vp), ('b_edge2', _vp), ('w_coor1', _vp), ('b_coor1', _vp), ('w_coor2', _vp),
                 ('b_coor2', _f32), ('w_edge_tc', _vp), ('edge_consts_host', _vp),
+                ('w_node_tc', _vp), ('node_consts_host', _vp), ('w_proj_tc', _vp), ('proj_bias_host', _vp),
                 ('w_node1', _vp), ('b_node1', _vp), ('node_ln_g', _vp), ('node_ln_b', _vp),
                 ('w_node2', _vp), ('b_node2', _vp),
                 ('skip_weight_h', _f32), ('x_connection_init', _f32), ('leaky_slope', _f32)]
@@ -50,6 +51,12 @@ PROTOTYPES = {
     'eqd_edge_stage': (C.c_int, [_G, _L, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'eqd_edge_stage_ffma': (C.c_int, [_G, _L, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'eqd_node_stage': (C.c_int, [_G, _L, _L, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'eqd_kv_blocks_bytes': (C.c_size_t, [_i32]),
+    'eqd_project_tc': (C.c_int, [_G, _L, _vp, _vp, _vp, _vp]),
+    'eqd_kv_blocks': (C.c_int, [_G, _vp, _i32, _i32, _i32, _vp, _vp]),
+    'eqd_attention_tc': (C.c_int, [_G, _vp, _vp, _vp, _vp]),
+    'eqd_node_mlp_tc': (C.c_int, [_G, _L, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'eqd_node_stage_tc': (C.c_int, [_G, _L, _L, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'eqd_iegmn_layer_forward': (C.c_int, [_G, _L, _L, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'eqd_keypoints': (C.c_int, [_G, _H, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
     'eqd_kabsch_apply': (C.c_int, [_G, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -1,0 +1,251 @@
+// Segmented cross attention of a 64-wide IEGMN layer (rigid_docking_model.py:46-64, 247-256) on the tensor
+// cores (tcgen05, bf16x6):   mu_i = sum_j softmax_j(q_i . k_j) v_j   over the partner protein's nodes j
+// (the per-pair block of the reference's dense masked softmax; no 1/sqrt(d)).
+//
+// A tile = 128 query nodes of one protein; two tile groups of 256 threads per CTA (2 threads per query row).
+// K and V of every node arrive as bf16x3 8-node blocks (written by the projection kernel), so a run of
+// 8 blocks (64 keys) is TMA-bulk-copied straight into shared memory as a UMMA B operand:
+//   S = Q K^T   : A = Q (TMEM, bf16x3), B = K blocks, K-major  (n = key, k = d)
+//   O += P V    : A = P (TMEM, bf16x3), B = V blocks, MN-major (k = key, n = d)
+// Two passes over the keys (row maxima first, then exp / P.V) instead of an online softmax: the extra S GEMMs
+// are cheap on the tensor pipe and O never has to be rescaled in TMEM.
+#include "tc_common.cuh"
+
+namespace eqd {
+
+#define AT_THREADS 512
+#define AT_KEYS 64            // keys per chunk = 8 blocks
+#define AT_CHUNK_BYTES 8192   // per split
+
+struct AtGroupSmem {
+  unsigned char k[2][3][AT_CHUNK_BYTES];  // double-buffered K chunks (3 splits)
+  unsigned char v[2][3][AT_CHUNK_BYTES];
+  float red[EQD_TM * 2];
+};
+struct AtSmem {
+  AtGroupSmem grp[2];
+  unsigned long long k_bar[2][2], v_bar[2][2], mma_bar[2];
+  unsigned int tmem_base;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, const unsigned char* __restrict__ kv, long kv_split_stride,
+                    float* __restrict__ mu) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  AtSmem& S = *reinterpret_cast<AtSmem*>(smem_raw);
+  const int tid = threadIdx.x, wg = tid >> 8, q = tid & 255, half = q >> 7, r = q & 127, warp = tid >> 5;
+  AtGroupSmem& G = S.grp[wg];
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&S.mma_bar[a], 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&S.k_bar[a][b], 1);
+        mbar_init(&S.v_bar[a][b], 1);
+      }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int wg_u = warp_u >> 3;
+  const bool issuer_warp = (warp_u & 7) == 0;
+  const unsigned tmem_wg = __shfl_sync(0xffffffffu, S.tmem_base, 0) + (unsigned)wg_u * 256;
+  const unsigned tmem = tmem_wg + ((unsigned)((warp & 3) * 32) << 16);
+  // columns: Q (A) 0..95 | S (fp32, 64) / P (A, 3x32) 96..191 | O 192..255
+  const unsigned k_saddr = smem_u32(S.grp[wg_u].k), v_saddr = smem_u32(S.grp[wg_u].v);
+  unsigned kph[2] = {0, 0}, vph[2] = {0, 0}, mph = 0;
+  const int B = g.n_pairs;
+  const unsigned char* k_g = kv;                              // which = 0
+  const unsigned char* v_g = kv + 3 * kv_split_stride;        // which = 1
+
+  auto load_chunk = [&](const unsigned char* src, unsigned char (*dst)[AT_CHUNK_BYTES], unsigned long long* bar, int blk0) {
+    if (q == 0) {
+      mbar_expect_tx(bar, 3 * AT_CHUNK_BYTES);
+#pragma unroll
+      for (int s = 0; s < 3; ++s) bulk_g2s(dst[s], src + s * kv_split_stride + (long)blk0 * 1024, AT_CHUNK_BYTES, bar);
+    }
+  };
+  // S = Q K^T for one 64-key chunk in K buffer `kb_`
+  auto issue_s = [&](int kb_) {
+    if (issuer_warp) {
+      tc_fence_after();
+      if (elect_one()) {
+        const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};
+        unsigned accum = 0;
+#pragma unroll
+        for (int pr = 0; pr < 6; ++pr)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            umma_ts(tmem_wg + 96, tmem_wg + pa[pr] * 32 + kk * 8,
+                    b_desc_ex(k_saddr + (kb_ * 3 + pb[pr]) * AT_CHUNK_BYTES + kk * 256, 128, 1024), accum);
+            accum = 1;
+          }
+        umma_commit(&S.mma_bar[wg_u]);
+      }
+      __syncwarp();
+    }
+  };
+  // O (+)= P V for one chunk in V buffer `vb_`
+  auto issue_pv = [&](int vb_, unsigned accum0) {
+    if (issuer_warp) {
+      tc_fence_after();
+      if (elect_one()) {
+        const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};
+        const unsigned idesc = umma_idesc(64, 1);  // B is MN-major: [key][d]
+        unsigned accum = accum0;
+#pragma unroll
+        for (int pr = 0; pr < 6; ++pr)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            umma_ts_i(tmem_wg + 192, tmem_wg + 96 + pa[pr] * 32 + kk * 8,
+                      b_desc_ex(v_saddr + (vb_ * 3 + pb[pr]) * AT_CHUNK_BYTES + kk * 2048, 1024, 128), idesc, accum);
+            accum = 1;
+          }
+        umma_commit(&S.mma_bar[wg_u]);
+      }
+      __syncwarp();
+    }
+  };
+  auto wait_mma = [&]() {
+    mbar_wait(&S.mma_bar[wg], mph);
+    mph ^= 1;
+    tc_fence_after();
+  };
+
+  for (int tile = blockIdx.x * 2 + wg; tile < g.n_node_tiles; tile += gridDim.x * 2) {
+    const int seg = g.node_tiles[2 * tile], node0 = g.node_tiles[2 * tile + 1];
+    const int nvalid = min(EQD_TM, g.seg_ptr[seg + 1] - node0);
+    const int pseg = seg < B ? seg + B : seg - B;
+    const int j0 = g.seg_ptr[pseg], j1 = g.seg_ptr[pseg + 1];
+    const int blk_lo = j0 >> 3, blk_hi = (j1 + 7) >> 3;
+    const int nchunks = (blk_hi - blk_lo + 7) >> 3;
+    const int node = node0 + r;
+    const bool valid = r < nvalid;
+    if (nchunks > 0) load_chunk(k_g, G.k[0], &S.k_bar[wg][0], blk_lo);
+    {  // Q row -> bf16x3 -> TMEM
+      float v[32];
+      const float4* sp = reinterpret_cast<const float4*>(proj + (long)node * 320 + 128 + half * 32);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        float4 t = valid ? sp[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[c4 * 4] = t.x; v[c4 * 4 + 1] = t.y; v[c4 * 4 + 2] = t.z; v[c4 * 4 + 3] = t.w;
+      }
+      store_half_split3(tmem + half * 16, v);
+    }
+    tc_fence_before();
+    wg_barrier(wg);
+    // ---------------- pass 1: row maxima ----------------------------------------------------------------
+    float mx = -INFINITY;
+    for (int c = 0; c < nchunks; ++c) {
+      const int kb_ = c & 1;
+      mbar_wait(&S.k_bar[wg][kb_], kph[kb_]);
+      kph[kb_] ^= 1;
+      issue_s(kb_);
+      // the other K buffer was last read by the S GEMM of chunk c-1, already waited for: prefetch into it
+      if (c + 1 < nchunks) load_chunk(k_g, G.k[kb_ ^ 1], &S.k_bar[wg][kb_ ^ 1], blk_lo + 8 * (c + 1));
+      else load_chunk(k_g, G.k[kb_ ^ 1], &S.k_bar[wg][kb_ ^ 1], blk_lo);   // first chunk of pass 2
+      wait_mma();
+      float s[32];
+      tmem_ld32f(tmem + 96 + half * 32, s);
+      const int key0 = (blk_lo + 8 * c) * 8 + half * 32;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        int kn = key0 + i;
+        mx = fmaxf(mx, (kn >= j0 && kn < j1) ? s[i] : -INFINITY);
+      }
+      tc_fence_before();
+      wg_barrier(wg);  // S drained before the next S GEMM overwrites it
+    }
+    G.red[r * 2 + half] = mx;
+    wg_barrier(wg);
+    mx = fmaxf(G.red[r * 2], G.red[r * 2 + 1]);
+    // ---------------- pass 2: P = exp(S - max), O += P V ----------------------------------------------------
+    float l = 0.f;
+    float o_acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
+    if (nchunks > 0) load_chunk(v_g, G.v[0], &S.v_bar[wg][0], blk_lo);
+    for (int c = 0; c < nchunks; ++c) {
+      const int kb_ = (nchunks + c) & 1, vb_ = c & 1;   // K buffers keep alternating after pass 1
+      mbar_wait(&S.k_bar[wg][kb_], kph[kb_]);
+      kph[kb_] ^= 1;
+      issue_s(kb_);
+      if (c + 1 < nchunks) {
+        load_chunk(k_g, G.k[kb_ ^ 1], &S.k_bar[wg][kb_ ^ 1], blk_lo + 8 * (c + 1));
+        load_chunk(v_g, G.v[vb_ ^ 1], &S.v_bar[wg][vb_ ^ 1], blk_lo + 8 * (c + 1));   // its last reader (P V of c-1) is done
+      }
+      wait_mma();
+      float s[32];
+      tmem_ld32f(tmem + 96 + half * 32, s);
+      const int key0 = (blk_lo + 8 * c) * 8 + half * 32;
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        int kn = key0 + i;
+        float pj = (kn >= j0 && kn < j1) ? expf(s[i] - mx) : 0.f;
+        s[i] = pj;
+        l4[i & 3] += pj;
+      }
+      l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      tc_fence_before();
+      wg_barrier(wg);  // every S value is in registers: the P splits may overwrite the S columns
+      store_half_split3(tmem + 96 + half * 16, s);
+      tc_fence_before();
+      wg_barrier(wg);
+      mbar_wait(&S.v_bar[wg][vb_], vph[vb_]);
+      vph[vb_] ^= 1;
+      issue_pv(vb_, 0u);
+      wait_mma();      // P (= the S region) and this V buffer are free again
+      // The tensor core truncates (round-toward-zero) every time it adds into an fp32 accumulator, a systematic
+      // bias that grows with the number of accumulation steps; each 64-key chunk is therefore accumulated on its
+      // own (4 full-magnitude steps) and the chunks are summed here with round-to-nearest FADDs.
+      {
+        float oc[32];
+        tmem_ld32f(tmem + 192 + half * 32, oc);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[i] += oc[i];
+      }
+    }
+    // ---------------- mu = O / l -----------------------------------------------------------------------------
+    G.red[r * 2 + half] = l;
+    wg_barrier(wg);
+    l = G.red[r * 2] + G.red[r * 2 + 1];
+    {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      if (valid) {
+        float4* dst = reinterpret_cast<float4*>(mu + (long)node * EQD_HID + half * 32);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4)
+          dst[c4] = make_float4(o_acc[c4 * 4] * inv, o_acc[c4 * 4 + 1] * inv, o_acc[c4 * 4 + 2] * inv, o_acc[c4 * 4 + 3] * inv);
+      }
+    }
+    tc_fence_before();
+    wg_barrier(wg);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base), "r"(512));
+}
+
+}  // namespace eqd
+
+extern "C" int eqd_attention_tc(const eqd_graph* g, const float* proj, const void* kv, float* mu, void* stream) {
+  if (!g || !proj || !kv || !mu) return EQD_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(kv) & 15) return EQD_ERR_BAD_ARG;
+  if (g->n_node_tiles <= 0) return EQD_OK;
+  size_t smem = sizeof(eqd::AtSmem) + 128;
+  cudaFuncSetAttribute(eqd::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int grid = (g->n_node_tiles + 1) / 2;
+  if (grid > 148) grid = 148;
+  long split_stride = (long)((g->n_nodes + 7) / 8 + 8) * 1024;
+  eqd::attention_tc_kernel<<<grid, AT_THREADS, smem, (cudaStream_t)stream>>>(*g, proj, reinterpret_cast<const unsigned char*>(kv),
+                                                                            split_stride, mu);
+  EQD_CUDA_LAUNCH_CHECK();
+  return EQD_OK;
+}

@@ -14,7 +14,7 @@
 //   GEMM2 (24 mma) -> msg (+bias) -> fp32 tile in smem (mean aggregation) and bf16x3 -> TMEM
 //   GEMM3 (24 mma) -> LeakyReLU, dot w4 -> phi ; x' = eta x0 + (1-eta) x + mean(x_rel phi) in fp64.
 // Per-edge activations never leave the SM; weights are read from HBM/L2 once per CTA.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace eqd {
 #define TC_THREADS 512
@@ -49,143 +49,6 @@ struct TcSmem {
 struct EdgeConsts {                       // per-layer vectors, passed by value (constant bank operands)
   float ln_g[64], ln_b[64], b2[64], b3[64], w4[64];
 };
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  unsigned addr = smem_u32(bar);
-  unsigned done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-  }
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src));
-}
-__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src));
-}
-__device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 256;" ::"r"(wg + 1) : "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major no-swizzle canonical B descriptor: LBO (K direction) = 1024 B, SBO (N direction) = 128 B
-__device__ __forceinline__ unsigned long long b_desc(unsigned saddr) {
-  return (unsigned long long)((saddr >> 4) & 0x3FFF) | ((unsigned long long)(1024 >> 4) << 16) |
-         ((unsigned long long)(128 >> 4) << 32) | (1ull << 46);
-}
-// D[128x64] (+)= A[tmem, 128x16 bf16] * B[smem desc, 64x16 bf16]^T
-__device__ __forceinline__ void umma_ts(unsigned d_tmem, unsigned a_tmem, unsigned long long bdesc, unsigned accum) {
-  const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc),
-      "r"(accum) : "memory");
-}
-// All 6 cross products of the bf16x3 splits, smallest terms first; A split s at a_base + s*a_split_cols.
-__device__ __forceinline__ void issue_gemm(unsigned d_tmem, unsigned a_base, unsigned a_split_cols, unsigned w_saddr,
-                                           unsigned w_split_bytes, int kblocks) {
-  const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};
-  unsigned accum = 0;
-#pragma unroll
-  for (int pr = 0; pr < 6; ++pr)
-    for (int kb = 0; kb < kblocks; ++kb) {
-      umma_ts(d_tmem, a_base + pa[pr] * a_split_cols + kb * 8, b_desc(w_saddr + pb[pr] * w_split_bytes + kb * 2048), accum);
-      accum = 1;
-    }
-}
-__device__ __forceinline__ bool elect_one() {
-  unsigned pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// ---- bf16x3 split of register tiles and TMEM stores / loads -------------------------------------
-__device__ __forceinline__ unsigned cvt_bf16x2(float hi, float lo) {
-  unsigned d;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-// (v0, v1) -> three packed bf16x2 words (v0 in the low half = even k)
-__device__ __forceinline__ void split3_pair(float v0, float v1, unsigned& p0, unsigned& p1, unsigned& p2) {
-  p0 = cvt_bf16x2(v1, v0);
-  float r0 = v0 - __uint_as_float(p0 << 16), r1 = v1 - __uint_as_float(p0 & 0xFFFF0000u);
-  p1 = cvt_bf16x2(r1, r0);
-  r0 -= __uint_as_float(p1 << 16);
-  r1 -= __uint_as_float(p1 & 0xFFFF0000u);
-  p2 = cvt_bf16x2(r1, r0);
-}
-__device__ __forceinline__ void tmem_st16(unsigned taddr, const unsigned (&v)[16]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-               "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
-}
-__device__ __forceinline__ void tmem_st8(unsigned taddr, const unsigned* v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
-               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32_nowait(unsigned taddr, unsigned (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
-      "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-}
-// this thread's 64-column accumulator row: two TMEM loads in flight, one wait
-__device__ __forceinline__ void tmem_ld64(unsigned taddr, float (&v)[64]) {
-  unsigned a[32], b[32];
-  tmem_ld32_nowait(taddr, a);
-  tmem_ld32_nowait(taddr + 32, b);
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    v[i] = __uint_as_float(a[i]);
-    v[32 + i] = __uint_as_float(b[i]);
-  }
-}
-// 32 fp32 values (this thread's half of its row) -> bf16x3 -> TMEM: split s lands at a_taddr + 32*s, 16 columns
-__device__ __forceinline__ void store_half_split3(unsigned a_taddr, const float (&v)[32]) {
-  unsigned p0[16], p1[16], p2[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) split3_pair(v[2 * c], v[2 * c + 1], p0[c], p1[c], p2[c]);
-  tmem_st16(a_taddr, p0);
-  tmem_st16(a_taddr + 32, p1);
-  tmem_st16(a_taddr + 64, p2);
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_st4(unsigned taddr, const unsigned* v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
-               "r"(v[3]) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32f(unsigned taddr, float (&v)[32]) {
-  unsigned a[32];
-  tmem_ld32_nowait(taddr, a);
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(a[i]);
-}
 
 // 512 threads = 2 tile groups x 256; in a group, thread (r = q & 127, half = q >> 7) owns columns
 // [32*half, 32*half+32) of edge row r (TMEM lane r): two threads per row keep the per-thread register

@@ -1,0 +1,235 @@
+// Node MLP of a 64-wide IEGMN layer (rigid_docking_model.py:319-337) on the tensor cores (tcgen05, bf16x6):
+//   h' = skip( W6 . LayerNorm(LeakyReLU(W5 . [h | aggr_msg | mu | h0] + b5)) + b6 )
+// Weight-stationary (W5: 64x272, W6: 64x64 as bf16x3 UMMA panels, 126 KB in shared memory), two tile groups of
+// 256 threads (2 threads per node row) running out of phase.  The 272-wide input is fed in 5 K-pieces.
+#include "tc_common.cuh"
+
+namespace eqd {
+
+#define NM_THREADS 512
+#define NM_W5_SPLIT 34816   // 64 x 272 bf16
+#define NM_W6_BASE 104448
+#define NM_W6_SPLIT 8192
+#define NM_W_BYTES 129024
+
+struct NmConsts { float b5[64], ln_g[64], ln_b[64], b6[64]; };
+
+struct NmSmem {
+  unsigned char w[NM_W_BYTES];
+  float red[2][EQD_TM * 4];
+  unsigned long long w_bar, a_bar[2][2];
+  unsigned int tmem_base;
+};
+
+__global__ void __launch_bounds__(NM_THREADS, 1)
+node_mlp_tc_kernel(int n_nodes, eqd_layer_params p, const __grid_constant__ NmConsts cst, const float* __restrict__ h_in,
+                   const float* __restrict__ aggr, const float* __restrict__ mu, const float* __restrict__ h0,
+                   float* __restrict__ h_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  NmSmem& S = *reinterpret_cast<NmSmem*>(smem_raw);
+  const int tid = threadIdx.x, wg = tid >> 8, q = tid & 255, half = q >> 7, r = q & 127, warp = tid >> 5;
+  const int ntiles = (n_nodes + EQD_TM - 1) / EQD_TM;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&S.w_bar, 1);
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) mbar_init(&S.a_bar[a][b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&S.w_bar, NM_W_BYTES);
+    bulk_g2s(S.w, p.w_node_tc, NM_W_BYTES, &S.w_bar);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int wg_u = warp_u >> 3;
+  const bool issuer_warp = (warp_u & 7) == 0;
+  const unsigned tmem_wg = __shfl_sync(0xffffffffu, S.tmem_base, 0) + (unsigned)wg_u * 256;
+  const unsigned tmem = tmem_wg + ((unsigned)((warp & 3) * 32) << 16);
+  // columns: D 0..63, A 64..159
+  const unsigned w_saddr = smem_u32(S.w);
+  mbar_wait(&S.w_bar, 0);
+  unsigned ph[2] = {0, 0};
+  const float slope = p.leaky_slope;
+  float* red = S.red[wg];
+
+  // MMAs of K-blocks [kb0, kb0+nkb) of W5 (or all of W6) reading A buffer `ab`, then arrive on a_bar[ab]
+  auto issue = [&](int ab, unsigned w_off, unsigned w_split, int nkb, unsigned accum0) {
+    if (issuer_warp) {
+      tc_fence_after();
+      if (elect_one()) {
+        issue_gemm(tmem_wg, tmem_wg + 64 + ab * 96, 32, w_saddr + w_off, w_split, nkb, accum0);
+        umma_commit(&S.a_bar[wg_u][ab]);
+      }
+      __syncwarp();
+    }
+  };
+  auto wait_a = [&](int ab) {
+    mbar_wait(&S.a_bar[wg][ab], ph[ab]);
+    ph[ab] ^= 1;
+    tc_fence_after();
+  };
+
+  for (int tile = blockIdx.x * 2 + wg; tile < ntiles; tile += gridDim.x * 2) {
+    const int node = tile * EQD_TM + r;
+    const bool valid = node < n_nodes;
+    float hskip[32];
+    auto load32 = [&](const float* base, int ld, int col0, float (&v)[32]) {
+      const float4* sp = reinterpret_cast<const float4*>(base + (long)node * ld + col0 + half * 32);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        float4 t = valid ? sp[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[c4 * 4] = t.x; v[c4 * 4 + 1] = t.y; v[c4 * 4 + 2] = t.z; v[c4 * 4 + 3] = t.w;
+      }
+    };
+    // ---- node_mlp.0 over [h | aggr | mu | h0] in 5 K-pieces ---------------------------------------------------
+    // The tensor core truncates (round-toward-zero) on every add into an fp32 accumulator: a bias that grows with
+    // the number of accumulation steps.  Each 64-wide piece is therefore its own accumulation (4 full-magnitude
+    // steps, like the edge-stage GEMMs) and the pieces are summed in registers with round-to-nearest FADDs.
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = cst.b5[half * 32 + c];
+    load32(h_in, EQD_HID, 0, hskip);
+    store_half_split3(tmem + 64 + half * 16, hskip);       // piece 0 (h) -> A
+    tc_fence_before();
+    wg_barrier(wg);
+    issue(0, 0, NM_W5_SPLIT, 4, 0);
+    {
+      float v[32], d[32];
+      auto drain = [&]() {                                  // D of the finished piece -> acc
+        wait_a(0);
+        tmem_ld32f(tmem + half * 32, d);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] += d[c];
+      };
+      load32(aggr, EQD_HID, 0, v);
+      drain();
+      store_half_split3(tmem + 64 + half * 16, v);         // piece 1 (aggr)
+      tc_fence_before();
+      wg_barrier(wg);
+      issue(0, 4 * 2048, NM_W5_SPLIT, 4, 0);
+      load32(mu, EQD_HID, 0, v);
+      drain();
+      store_half_split3(tmem + 64 + half * 16, v);         // piece 2 (mu)
+      tc_fence_before();
+      wg_barrier(wg);
+      issue(0, 8 * 2048, NM_W5_SPLIT, 4, 0);
+      load32(h0, EQD_H0_PAD, 0, v);
+      drain();
+      store_half_split3(tmem + 64 + half * 16, v);         // piece 3 (h0[0:64])
+      tc_fence_before();
+      wg_barrier(wg);
+      issue(0, 12 * 2048, NM_W5_SPLIT, 4, 0);
+      drain();
+      // piece 4: h0[64:72] + 8 zero columns (K = 16): the half-0 threads write 8 columns per split
+      if (half == 0) {
+        float t[16];
+        const float4* sp = reinterpret_cast<const float4*>(h0 + (long)node * EQD_H0_PAD + 64);
+        float4 a = valid ? sp[0] : make_float4(0.f, 0.f, 0.f, 0.f), b = valid ? sp[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = b.x; t[5] = b.y; t[6] = b.z; t[7] = b.w;
+#pragma unroll
+        for (int c = 8; c < 16; ++c) t[c] = 0.f;
+        unsigned p0[8], p1[8], p2[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) split3_pair(t[2 * c], t[2 * c + 1], p0[c], p1[c], p2[c]);
+        tmem_st8(tmem + 64, p0);
+        tmem_st8(tmem + 64 + 32, p1);
+        tmem_st8(tmem + 64 + 64, p2);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      tc_fence_before();
+      wg_barrier(wg);
+      issue(0, 16 * 2048, NM_W5_SPLIT, 1, 0);
+      drain();
+    }
+    // ---- + bias, LeakyReLU, LayerNorm -> bf16x3 -> A1 ; node_mlp.4 ---------------------------------------------
+    {
+      float v[32];
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        v[c] = lrelu(acc[c], slope);
+        s4[c & 3] += v[c];
+      }
+      const float mh = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.f / 32.f);
+      float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float d = v[c] - mh;
+        q4[c & 3] = fmaf(d, d, q4[c & 3]);
+      }
+      red[(r * 2 + half) * 2 + 0] = mh;
+      red[(r * 2 + half) * 2 + 1] = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+      tc_fence_before();
+      wg_barrier(wg);
+      const float m0 = red[r * 4 + 0], m1 = red[r * 4 + 2];
+      const float mean = 0.5f * (m0 + m1);
+      const float dm = m0 - m1;
+      const float var = (red[r * 4 + 1] + red[r * 4 + 3] + dm * dm * 16.f) * (1.f / 64.f);  // Chan et al. combination
+      const float rstd = 1.f / sqrtf(var + 1e-5f);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[c] = (v[c] - mean) * rstd * cst.ln_g[half * 32 + c] + cst.ln_b[half * 32 + c];
+      store_half_split3(tmem + 64 + half * 16, v);
+    }
+    tc_fence_before();
+    wg_barrier(wg);
+    issue(0, NM_W6_BASE, NM_W6_SPLIT, 4, 0);
+    wait_a(0);
+    {
+      float v[32];
+      tmem_ld32f(tmem + half * 32, v);
+      const float sk = p.skip_weight_h, sk1 = 1.f - p.skip_weight_h;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[c] = sk * (v[c] + cst.b6[half * 32 + c]) + sk1 * hskip[c];  // :332-334
+      if (valid) {
+        float4* o = reinterpret_cast<float4*>(h_out + (long)node * EQD_HID + half * 32);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) o[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+      }
+    }
+    tc_fence_before();
+    wg_barrier(wg);  // D and both A buffers are free for the next tile
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base), "r"(512));
+}
+
+}  // namespace eqd
+
+extern "C" int eqd_node_mlp_tc(const eqd_graph* g, const eqd_layer_params* p, const float* h_in, const float* aggr,
+                               const float* mu, const float* h0, float* h_out, void* stream) {
+  if (!g || !p || !h_in || !aggr || !mu || !h0 || !h_out) return EQD_ERR_BAD_ARG;
+  if (p->dh != 64 || p->dhp != 64) return EQD_ERR_UNSUPPORTED;
+  if (!p->w_node_tc || !p->node_consts_host || (reinterpret_cast<uintptr_t>(p->w_node_tc) & 15)) return EQD_ERR_BAD_ARG;
+  if (g->n_nodes <= 0) return EQD_OK;
+  eqd::NmConsts cst;
+  memcpy(&cst, p->node_consts_host, sizeof(cst));
+  int ntiles = (g->n_nodes + EQD_TM - 1) / EQD_TM;
+  size_t smem = sizeof(eqd::NmSmem) + 128;
+  cudaFuncSetAttribute(eqd::node_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int grid = (ntiles + 1) / 2;
+  if (grid > 148) grid = 148;
+  eqd::node_mlp_tc_kernel<<<grid, NM_THREADS, smem, (cudaStream_t)stream>>>(g->n_nodes, *p, cst, h_in, aggr, mu, h0, h_out);
+  EQD_CUDA_LAUNCH_CHECK();
+  return EQD_OK;
+}
+
+extern "C" int eqd_project_tc(const eqd_graph*, const eqd_layer_params*, const float*, float*, void*, void*);
+extern "C" int eqd_attention_tc(const eqd_graph*, const float*, const void*, float*, void*);
+
+extern "C" int eqd_node_stage_tc(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next,
+                                 const float* h_in, const float* h0, const float* proj, const float* aggr, void* kv,
+                                 float* mu, float* h_out, float* proj_next, void* stream) {
+  if (!g || !p || !kv || !mu) return EQD_ERR_BAD_ARG;
+  if (p_next && !proj_next) return EQD_ERR_BAD_ARG;
+  int rc = eqd_attention_tc(g, proj, kv, mu, stream);
+  if (rc) return rc;
+  rc = eqd_node_mlp_tc(g, p, h_in, aggr, mu, h0, h_out, stream);
+  if (rc) return rc;
+  if (p_next) rc = eqd_project_tc(g, p_next, h_out, proj_next, kv, stream);
+  return rc;
+}

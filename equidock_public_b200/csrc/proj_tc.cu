@@ -1,0 +1,185 @@
+// Node projections of a 64-wide layer on the tensor cores (tcgen05, bf16x6):
+//   proj[n] = [Psrc | Pdst | Q | K | V] = act(h[n] . Wp + b)      (5 groups of 64 columns, see eqd_layer_params)
+// plus, for the tensor-core attention of the same layer, K and V of every node as bf16x3 in 8-node blocks
+//   kv[split][which][n/8][d/8][n%8][d%8]   (1 KB per 8 nodes; a run of blocks is a ready UMMA B operand).
+// Weight-stationary: the 5x3 bf16 panels (120 KB) sit in shared memory for the life of the CTA; two tile
+// groups of 256 threads (2 threads per node row) ping-pong two TMEM accumulators.
+#include "tc_common.cuh"
+
+namespace eqd {
+
+#define PJ_THREADS 512
+#define PJ_W_BYTES 122880   // 5 groups x 3 splits x 8192
+#define PJ_GROUP_BYTES 24576
+
+struct PjConsts { float b[320]; };
+
+struct PjSmem {
+  unsigned char w[PJ_W_BYTES];
+  unsigned long long w_bar, d_bar[2][2];
+  unsigned int tmem_base;
+};
+
+// bf16x3 block-layout store of 32 consecutive channels [half*32, +32) of node `node`
+__device__ __forceinline__ void store_kv_blocks(unsigned char* __restrict__ kv, long split_stride, int node, int half,
+                                                const float (&v)[32]) {
+  unsigned p0[16], p1[16], p2[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) split3_pair(v[2 * c], v[2 * c + 1], p0[c], p1[c], p2[c]);
+  unsigned char* base = kv + (long)(node >> 3) * 1024 + (node & 7) * 16 + half * 512;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {  // 4 groups of 8 channels = 16 bytes each
+    *reinterpret_cast<uint4*>(base + j * 128) = make_uint4(p0[4 * j], p0[4 * j + 1], p0[4 * j + 2], p0[4 * j + 3]);
+    *reinterpret_cast<uint4*>(base + split_stride + j * 128) = make_uint4(p1[4 * j], p1[4 * j + 1], p1[4 * j + 2], p1[4 * j + 3]);
+    *reinterpret_cast<uint4*>(base + 2 * split_stride + j * 128) = make_uint4(p2[4 * j], p2[4 * j + 1], p2[4 * j + 2], p2[4 * j + 3]);
+  }
+}
+
+__global__ void __launch_bounds__(PJ_THREADS, 1)
+project_tc_kernel(int n_nodes, eqd_layer_params p, const __grid_constant__ PjConsts cst, const float* __restrict__ h,
+                  float* __restrict__ proj, unsigned char* __restrict__ kv, long kv_split_stride) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  PjSmem& S = *reinterpret_cast<PjSmem*>(smem_raw);
+  const int tid = threadIdx.x, wg = tid >> 8, q = tid & 255, half = q >> 7, r = q & 127, warp = tid >> 5;
+  const int ntiles = (n_nodes + EQD_TM - 1) / EQD_TM;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&S.w_bar, 1);
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) mbar_init(&S.d_bar[a][b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&S.w_bar, PJ_W_BYTES);
+    bulk_g2s(S.w, p.w_proj_tc, PJ_W_BYTES, &S.w_bar);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int wg_u = warp_u >> 3;
+  const bool issuer_warp = (warp_u & 7) == 0;
+  const unsigned tmem_wg = __shfl_sync(0xffffffffu, S.tmem_base, 0) + (unsigned)wg_u * 256;
+  const unsigned tmem = tmem_wg + ((unsigned)((warp & 3) * 32) << 16);
+  const unsigned a_col = tmem + 128;  // D0: 0..63, D1: 64..127, A: 128..223
+  const unsigned w_saddr = smem_u32(S.w);
+  mbar_wait(&S.w_bar, 0);
+  unsigned ph[2] = {0, 0};
+  const float slope = p.leaky_slope;
+
+  auto issue = [&](int grp) {  // 24 MMAs of projection group `grp` into D[grp & 1]
+    if (issuer_warp) {
+      tc_fence_after();
+      if (elect_one()) {
+        issue_gemm(tmem_wg + (grp & 1) * 64, tmem_wg + 128, 32, w_saddr + grp * PJ_GROUP_BYTES, 8192, 4);
+        umma_commit(&S.d_bar[wg_u][grp & 1]);
+      }
+      __syncwarp();
+    }
+  };
+
+  for (int tile = blockIdx.x * 2 + wg; tile < ntiles; tile += gridDim.x * 2) {
+    const int node0 = tile * EQD_TM;
+    const int node = node0 + r;
+    const bool valid = node < n_nodes;
+    {
+      float v[32];
+      const float4* hp = reinterpret_cast<const float4*>(h + (long)node * EQD_HID + half * 32);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        float4 t = valid ? hp[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[c4 * 4] = t.x; v[c4 * 4 + 1] = t.y; v[c4 * 4 + 2] = t.z; v[c4 * 4 + 3] = t.w;
+      }
+      store_half_split3(a_col + half * 16, v);
+    }
+    tc_fence_before();
+    wg_barrier(wg);
+    issue(0);
+    issue(1);
+#pragma unroll 1
+    for (int grp = 0; grp < 5; ++grp) {
+      const int d = grp & 1;
+      mbar_wait(&S.d_bar[wg][d], ph[d]);
+      ph[d] ^= 1;
+      tc_fence_after();
+      float v[32];
+      tmem_ld32f(tmem + d * 64 + half * 32, v);
+      tc_fence_before();
+      wg_barrier(wg);                       // every thread has drained D[d]
+      if (grp + 2 < 5) issue(grp + 2);      // refill it while this group's epilogue runs
+      const bool act = (grp == 2 || grp == 3);  // Q, K carry the LeakyReLU
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float t = v[c] + cst.b[grp * 64 + half * 32 + c];
+        v[c] = act ? lrelu(t, slope) : t;
+      }
+      if (valid) {
+        float4* o = reinterpret_cast<float4*>(proj + (long)node * 320 + grp * 64 + half * 32);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) o[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+        if (grp >= 3 && kv != nullptr) store_kv_blocks(kv + (long)(grp - 3) * 3 * kv_split_stride, kv_split_stride, node, half, v);
+      }
+    }
+    tc_fence_before();
+    wg_barrier(wg);  // A may be overwritten by the next tile
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base), "r"(512));
+}
+
+// fp32 K / V columns of a projection buffer -> bf16x3 8-node blocks (used after the FFMA layer-0 node stage)
+__global__ void kv_blocks_kernel(int n_nodes, const float* __restrict__ proj, int pw, int koff, int voff,
+                                 unsigned char* __restrict__ kv, long kv_split_stride) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (node, which, half)
+  int node = idx >> 2, which = (idx >> 1) & 1, half = idx & 1;
+  if (node >= n_nodes) return;
+  const float4* src = reinterpret_cast<const float4*>(proj + (long)node * pw + (which ? voff : koff) + half * 32);
+  float v[32];
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) {
+    float4 t = src[c4];
+    v[c4 * 4] = t.x; v[c4 * 4 + 1] = t.y; v[c4 * 4 + 2] = t.z; v[c4 * 4 + 3] = t.w;
+  }
+  store_kv_blocks(kv + (long)which * 3 * kv_split_stride, kv_split_stride, node, half, v);
+}
+
+}  // namespace eqd
+
+extern "C" size_t eqd_kv_blocks_bytes(int32_t n_nodes) {
+  // [which 2][split 3][ceil(n/8) + 8 pad groups][1024 B]; the pad groups must be zero (they feed P.V as 0 x V)
+  return (size_t)6 * ((size_t)(n_nodes + 7) / 8 + 8) * 1024;
+}
+
+extern "C" int eqd_project_tc(const eqd_graph* g, const eqd_layer_params* p, const float* h, float* proj, void* kv,
+                              void* stream) {
+  if (!g || !p || !h || !proj) return EQD_ERR_BAD_ARG;
+  if (p->dh != 64 || p->dhp != 64) return EQD_ERR_UNSUPPORTED;
+  if (!p->w_proj_tc || !p->proj_bias_host || (reinterpret_cast<uintptr_t>(p->w_proj_tc) & 15)) return EQD_ERR_BAD_ARG;
+  if (g->n_nodes <= 0) return EQD_OK;
+  eqd::PjConsts cst;
+  memcpy(&cst, p->proj_bias_host, sizeof(cst));
+  int ntiles = (g->n_nodes + EQD_TM - 1) / EQD_TM;
+  size_t smem = sizeof(eqd::PjSmem) + 128;
+  cudaFuncSetAttribute(eqd::project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int grid = (ntiles + 1) / 2;
+  if (grid > 148) grid = 148;
+  long split_stride = (long)((g->n_nodes + 7) / 8 + 8) * 1024;
+  eqd::project_tc_kernel<<<grid, PJ_THREADS, smem, (cudaStream_t)stream>>>(g->n_nodes, *p, cst, h, proj,
+                                                                          reinterpret_cast<unsigned char*>(kv), split_stride);
+  EQD_CUDA_LAUNCH_CHECK();
+  return EQD_OK;
+}
+
+extern "C" int eqd_kv_blocks(const eqd_graph* g, const float* proj, int32_t pw, int32_t koff, int32_t voff, void* kv,
+                             void* stream) {
+  if (!g || !proj || !kv) return EQD_ERR_BAD_ARG;
+  if (g->n_nodes <= 0) return EQD_OK;
+  long split_stride = (long)((g->n_nodes + 7) / 8 + 8) * 1024;
+  int total = g->n_nodes * 4;
+  eqd::kv_blocks_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g->n_nodes, proj, pw, koff, voff,
+                                                                                reinterpret_cast<unsigned char*>(kv), split_stride);
+  EQD_CUDA_LAUNCH_CHECK();
+  return EQD_OK;
+}

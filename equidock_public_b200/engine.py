@@ -79,7 +79,19 @@ class PackedLayer:
         assert w_edge_tc.numel() * 2 == 67584
         self.edge_consts_host = torch.stack([f('edge_mlp.3.weight'), f('edge_mlp.3.bias'), f('edge_mlp.4.bias'),
                                              f('coors_mlp.0.bias'), f('coors_mlp.4.weight').reshape(-1)]).cpu().contiguous()
+        tc = {}
+        self.node_consts_host = self.proj_bias_host = None
+        if dh == nat.HID:  # tensor-core node stage panels (64-wide layers)
+            w5p = z(64, 272)
+            w5p[:, :261] = w5
+            tc['w_node_tc'] = torch.cat([umma_bf16x3(w5p), umma_bf16x3(w6)]).contiguous()
+            groups = [w1[:, 0:64], w1[:, 64:128], wq, wk, wv]
+            tc['w_proj_tc'] = torch.cat([umma_bf16x3(gw.contiguous()) for gw in groups]).contiguous()
+            assert tc['w_node_tc'].numel() * 2 == 129024 and tc['w_proj_tc'].numel() * 2 == 122880
+            self.node_consts_host = torch.stack([b5, f('node_mlp.3.weight'), f('node_mlp.3.bias'), b6]).cpu().contiguous()
+            self.proj_bias_host = b_proj.cpu().contiguous()
         self.t = {
+            **tc,
             'w_proj': w_proj, 'b_proj': b_proj, 'w_edge1': w_edge1,
             'edge_ln_g': f('edge_mlp.3.weight'), 'edge_ln_b': f('edge_mlp.3.bias'),
             'w_edge2': f('edge_mlp.4.weight').t().contiguous(), 'b_edge2': f('edge_mlp.4.bias'),
@@ -94,6 +106,9 @@ class PackedLayer:
         for k, v in self.t.items():
             setattr(s, k, v.data_ptr())
         s.edge_consts_host = self.edge_consts_host.data_ptr()
+        if self.node_consts_host is not None:
+            s.node_consts_host = self.node_consts_host.data_ptr()
+            s.proj_bias_host = self.proj_bias_host.data_ptr()
         s.b_coor2 = float(sd['coors_mlp.4.bias'].detach().reshape(-1)[0].item())
         s.skip_weight_h, s.x_connection_init, s.leaky_slope = skip_weight_h, x_connection_init, leaky_slope
         self.struct = s
@@ -192,9 +207,14 @@ class IEGMNEngine:
 
     @staticmethod
     def launches_per_forward(n_layers: int) -> int:
-        """Kernels of csrc/ launched by one forward: embed, project, (edge, node) x L, head_mean,
-        tile_ptr, keypoints, keypoint_cov, kabsch_apply."""
-        return 2 + 2 * n_layers + 5
+        """Kernels of csrc/ launched by one forward: embed, project (layer 0), per layer edge stage + node stage
+        (layer 0: fp32 node kernel + K/V blocks; 64-wide layers: attention, node MLP, next projections),
+        then head_mean, tile_ptr, keypoints, keypoint_cov, kabsch_apply."""
+        n = 2 + 5
+        for li in range(n_layers):
+            last = li == n_layers - 1
+            n += 1 + ((1 + (0 if last else 1)) if li == 0 else (2 + (0 if last else 1)))
+        return n
 
     def __init__(self, device):
         self.device = torch.device(device)
@@ -221,6 +241,12 @@ class IEGMNEngine:
         pa, pb = torch.empty(N, 128 + 3 * nat.H0_PAD, **f32), torch.empty(N, 128 + 3 * nat.H0_PAD, **f32)
         aggr = torch.empty(N, nat.HID, **f32)
         status = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+        mu = torch.empty(N, nat.HID, **f32)
+        kv_bytes = lib.eqd_kv_blocks_bytes(N)
+        kv = torch.empty(kv_bytes, dtype=torch.uint8, device=dev)
+        # rows never written (tail of the last 8-node block + the 8 pad blocks of each (K|V, split) plane) reach
+        # the P.V MMA as 0 x V: they must be finite
+        kv.view(6, -1)[:, (N // 8) * 1024:].zero_()
         nat.check(lib.eqd_embed(g, nat.ptr(emb), nat.ptr(res_l), nat.ptr(res_r), nat.ptr(mu_l), nat.ptr(mu_r),
                                 nat.ptr(x_l), nat.ptr(x_r), nat.ptr(h0), nat.ptr(x0), st), 'eqd_embed')
         nat.check(lib.eqd_project(g, C.byref(layers[0].struct), nat.ptr(h0), nat.H0_PAD, nat.ptr(pa), st),
@@ -231,20 +257,25 @@ class IEGMNEngine:
             nxt = layers[li + 1] if li + 1 < len(layers) else None
             lp = C.byref(lay.struct)
             lpn = C.byref(nxt.struct) if nxt is not None else None
-            if stage_timer is None:
-                nat.check(lib.eqd_iegmn_layer_forward(
-                    g, lp, lpn, nat.ptr(h_in), ldh, nat.ptr(h0), nat.ptr(x_in), nat.ptr(x0), nat.ptr(pa), nat.ptr(pb),
-                    nat.ptr(aggr), nat.ptr(h_out), nat.ptr(x_out), nat.ptr(status), st),
-                    f'eqd_iegmn_layer_forward[{li}]')
-            else:  # same two launches, bracketed by CUDA events on the launching stream
-                stage_timer.begin('edge_stage', li)
-                nat.check(lib.eqd_edge_stage(g, lp, nat.ptr(pa), nat.ptr(x_in), nat.ptr(x0), nat.ptr(aggr),
-                                             nat.ptr(x_out), nat.ptr(status), st), f'eqd_edge_stage[{li}]')
-                stage_timer.end('edge_stage', li)
-                stage_timer.begin('node_stage', li)
+            tmr = stage_timer
+            if tmr is not None:
+                tmr.begin('edge_stage', li)
+            nat.check(lib.eqd_edge_stage(g, lp, nat.ptr(pa), nat.ptr(x_in), nat.ptr(x0), nat.ptr(aggr),
+                                         nat.ptr(x_out), nat.ptr(status), st), f'eqd_edge_stage[{li}]')
+            if tmr is not None:
+                tmr.end('edge_stage', li)
+                tmr.begin('node_stage', li)
+            if lay.dh == nat.HID:   # tensor-core node stage: attention, node MLP, next layer's projections + K/V blocks
+                nat.check(lib.eqd_node_stage_tc(g, lp, lpn, nat.ptr(h_in), nat.ptr(h0), nat.ptr(pa), nat.ptr(aggr),
+                                                nat.ptr(kv), nat.ptr(mu), nat.ptr(h_out), nat.ptr(pb), st),
+                          f'eqd_node_stage_tc[{li}]')
+            else:                   # 69-wide layer 0: fp32 CUDA-core node stage (fused projections), then K/V blocks
                 nat.check(lib.eqd_node_stage(g, lp, lpn, nat.ptr(h_in), ldh, nat.ptr(h0), nat.ptr(pa), nat.ptr(aggr),
                                              nat.ptr(h_out), nat.ptr(pb), st), f'eqd_node_stage[{li}]')
-                stage_timer.end('node_stage', li)
+                if nxt is not None:
+                    nat.check(lib.eqd_kv_blocks(g, nat.ptr(pb), 320, 192, 256, nat.ptr(kv), st), 'eqd_kv_blocks')
+            if tmr is not None:
+                tmr.end('node_stage', li)
             pa, pb = pb, pa
             h_in, ldh, x_in = h_out, nat.HID, x_out
             h_out = hb if h_out is ha else ha

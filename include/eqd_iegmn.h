@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define EQD_ABI_VERSION 2
+#define EQD_ABI_VERSION 3
 
 #define EQD_EDGE_FEATS 27     /* input_edge_feats_dim, protein_utils.py:71-86 + :373-389 */
 #define EQD_N_RBF 15          /* all_sigmas_dist = 1.5**s, rigid_docking_model.py:116 */
@@ -106,6 +106,16 @@ typedef struct eqd_layer_params {
   /* HOST pointer to [5][64] floats: edge_ln_g, edge_ln_b, b_edge2, b_coor1, w_coor2 (copied into the kernel's
    * constant parameter space at launch). */
   const float* edge_consts_host;
+  /* tensor-core node stage (dh == 64 layers only; NULL for the 69-wide layer 0). Same bf16x3 UMMA panels:
+   *   w_node_tc : node_mlp.0.weight padded to [64][272] (K order h | aggr | mu | h0(69) | 0) at base 0, split
+   *               34816 B; node_mlp.4.weight [64][64] at base 104448, split 8192 B            (129024 B)
+   *   w_proj_tc : this layer's projection [Psrc|Pdst|Q|K|V] as 5 groups x 3 splits x 8192 B   (122880 B)
+   *   node_consts_host : HOST [4][64] = node_mlp.0.bias, node_mlp.3.weight, node_mlp.3.bias, node_mlp.4.bias
+   *   proj_bias_host   : HOST [320]   = b_proj                                                           */
+  const void* w_node_tc;
+  const float* node_consts_host;
+  const void* w_proj_tc;
+  const float* proj_bias_host;
   const float* w_node1;       /* [dhp+64+dhp+72][dhp] node_mlp.0.weight^T, row blocks [h | aggr_msg | mu | h0] */
   const float* b_node1;       /* [dhp] */
   const float* node_ln_g;     /* [dhp] node_mlp.3.weight (pad 0) */
@@ -164,6 +174,28 @@ int eqd_edge_stage_ffma(const eqd_graph* g, const eqd_layer_params* p, const flo
 int eqd_node_stage(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next,
                    const float* h_in, int32_t ldh, const float* h0, const float* proj,
                    const float* aggr, float* h_out, float* proj_next, void* stream);
+
+/* ---- tensor-core node stage (tcgen05, layers with dh == 64) ---------------------------------------------
+ * K and V of every node travel as bf16x3 "8-node blocks": kv[which 2 (K,V)][split 3][n/8 (+8 zero pad
+ * blocks)][d/8][n%8][d%8] bf16 (1 KB per block), so a run of blocks is a ready UMMA B operand for TMA.   */
+size_t eqd_kv_blocks_bytes(int32_t n_nodes);
+/* proj[n][320] = [Psrc|Pdst|Q|K|V](h[n]) for a dh==64 layer, plus its K/V blocks (kv may be NULL). */
+int eqd_project_tc(const eqd_graph* g, const eqd_layer_params* p, const float* h /*[n][64]*/, float* proj,
+                   void* kv, void* stream);
+/* K/V blocks from the fp32 columns of an existing projection buffer (row stride pw floats). */
+int eqd_kv_blocks(const eqd_graph* g, const float* proj, int32_t pw, int32_t koff, int32_t voff, void* kv,
+                  void* stream);
+/* mu[n][64] = softmax_j(q_n . k_j) v_j over the partner protein (:46-64, 247-256); proj row stride 320. */
+int eqd_attention_tc(const eqd_graph* g, const float* proj, const void* kv, float* mu, void* stream);
+/* h_out = skip(node_mlp([h | aggr | mu | h0])) (:319-337). */
+int eqd_node_mlp_tc(const eqd_graph* g, const eqd_layer_params* p, const float* h_in, const float* aggr,
+                    const float* mu, const float* h0, float* h_out, void* stream);
+/* Node stage of a dh==64 layer on the tensor cores = attention + node MLP (+ the next layer's projections and
+ * K/V blocks when p_next != NULL).  kv holds this layer's K/V blocks on entry, the next layer's on exit;
+ * mu is [n][64] scratch.                                                                                   */
+int eqd_node_stage_tc(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next,
+                      const float* h_in, const float* h0, const float* proj, const float* aggr, void* kv,
+                      float* mu, float* h_out, float* proj_next, void* stream);
 
 /* One whole IEGMN_Layer.forward = eqd_edge_stage + eqd_node_stage (proj must hold this layer's
  * projections on entry; holds the next layer's on exit when p_next != NULL).                  */

@@ -163,8 +163,8 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const float* __restrict__
 int main() {
   std::vector<float> A(128 * K_DIM), W(N_DIM * K_DIM), D(128 * N_DIM, -1.f);
   srand(1);
-  for (auto& v : A) v = (rand() / (float)RAND_MAX - 0.5f) * 4.f;
-  for (auto& v : W) v = (rand() / (float)RAND_MAX - 0.5f) * 0.5f;
+  for (auto& v : A) v = (rand() / (float)RAND_MAX) * 2.f + 0.1f;
+  for (auto& v : W) v = (rand() / (float)RAND_MAX) * 0.5f + 0.01f;
   float *dA, *dW, *dD;
   cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dW, W.size() * 4); cudaMalloc(&dD, D.size() * 4);
   cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
@@ -173,17 +173,21 @@ int main() {
   cudaError_t e = cudaDeviceSynchronize();
   printf("kernel status: %s\n", cudaGetErrorString(e));
   cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
-  double max_err = 0, max_err32 = 0, max_ref = 0;
+  double max_err = 0, max_err32 = 0, max_ref = 0, bias = 0, bias32 = 0, rms = 0, rms32 = 0;
   for (int m = 0; m < 128; ++m)
     for (int n = 0; n < N_DIM; ++n) {
       double ref = 0; float ref32 = 0.f;
       for (int k = 0; k < K_DIM; ++k) { ref += (double)A[m * K_DIM + k] * W[n * K_DIM + k]; ref32 = fmaf(A[m * K_DIM + k], W[n * K_DIM + k], ref32); }
-      max_err = fmax(max_err, fabs(D[m * N_DIM + n] - ref));
-      max_err32 = fmax(max_err32, fabs((double)ref32 - ref));
+      double e = D[m * N_DIM + n] - ref, e32 = (double)ref32 - ref, sg = ref >= 0 ? 1.0 : -1.0;
+      max_err = fmax(max_err, fabs(e));
+      max_err32 = fmax(max_err32, fabs(e32));
       max_ref = fmax(max_ref, fabs(ref));
+      bias += e * sg; bias32 += e32 * sg; rms += e * e; rms32 += e32 * e32;
     }
+  int cnt = 128 * N_DIM;
   printf("max|D - fp64 ref| = %.3e  (plain fp32 FMA loop: %.3e, max|ref| = %.3f)  D[0][0..3] = %f %f %f %f\n", max_err, max_err32,
          max_ref, D[0], D[1], D[2], D[3]);
+  printf("signed bias toward larger magnitude: tc %.3e  fma %.3e ; rms: tc %.3e  fma %.3e\n", bias / cnt, bias32 / cnt, sqrt(rms / cnt), sqrt(rms32 / cnt));
   printf(max_err < 1e-5 ? "PROBE PASS\n" : "PROBE FAIL\n");
   return 0;
 }

@@ -44,7 +44,8 @@ def test_struct_layouts_are_natural_c_layouts():
     assert nat.EqdGraph.seg_ptr.offset == 24 and nat.EqdGraph.node_tiles.offset == 80
     assert nat.EqdLayerParams.w_proj.offset == 8 and nat.EqdLayerParams.b_coor2.offset == 8 + 10 * 8
     assert nat.EqdLayerParams.w_edge_tc.offset == 96 and nat.EqdLayerParams.edge_consts_host.offset == 104
-    assert nat.EqdLayerParams.w_node1.offset == 112
+    assert nat.EqdLayerParams.w_node_tc.offset == 112 and nat.EqdLayerParams.proj_bias_host.offset == 136
+    assert nat.EqdLayerParams.w_node1.offset == 144
     assert ctypes.sizeof(nat.EqdHeadParams) == 4 * 8 + 8
 
 
@@ -162,4 +163,4 @@ def test_unsupported_configurations_raise():
 
 
 def test_launch_accounting():
-    assert IEGMNEngine.launches_per_forward(8) == 23 and IEGMNEngine.launches_per_forward(5) == 17
+    assert IEGMNEngine.launches_per_forward(8) == 37 and IEGMNEngine.launches_per_forward(5) == 25
