@@ -254,8 +254,13 @@ def run_engine(args, rank, local_rank, world):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        out = model(dev_batch, 0)
+    pending = None
+    for _ in range(args.steps):          # two steps in flight: step k is launched before step k-1's status words are read
+        nxt = model.forward_async(dev_batch, 0)
+        if pending is not None:
+            pending.result()
+        pending = nxt
+    pending.result()
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None

@@ -11,9 +11,11 @@
 //   GEMM1 (18 tcgen05.mma, B = edge_mlp.0.weight[:, 2dh:] bf16x3 resident in smem)
 //     -> + gathered Psrc[src] + Pdst[dst] (cp.async into smem), LeakyReLU, LayerNorm (one row per
 //        thread: no shuffles) -> bf16x3 -> TMEM
-//   GEMM2 (24 mma) -> msg (+bias) -> fp32 tile in smem (mean aggregation) and bf16x3 -> TMEM
-//   GEMM3 (24 mma) -> LeakyReLU, dot w4 -> phi ; x' = eta x0 + (1-eta) x + mean(x_rel phi) in fp64.
+//   GEMM2+3 (24 mma, N=128: [W2 ; W3 W2] on the same A) -> msg (+bias) -> fp32 tile in smem (mean aggregation)
+//     and the coordinate MLP's hidden layer -> LeakyReLU, dot w4 -> phi ; x' = eta x0 + (1-eta) x + mean(x_rel phi) in fp64.
 // Per-edge activations never leave the SM; weights are read from HBM/L2 once per CTA.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace eqd {
@@ -22,9 +24,8 @@ namespace eqd {
 #define TC_LD 68              // fp32 row stride of the staging / msg tile
 #define TC_W_BYTES 67584      // 3 splits x (6144 + 8192 + 8192)
 #define TC_W1_SPLIT 6144
-#define TC_W2_BASE 18432
-#define TC_W3_BASE 43008
-#define TC_W23_SPLIT 8192
+#define TC_W23_BASE 18432    // [W2 ; W3 W2] stacked, N = 128
+#define TC_W23_SPLIT 16384
 #define TC_HE_STAGE_FLOATS (EQD_TM * EQD_EDGE_FEATS + 16)
 
 struct TcWgSmem {                         // per warpgroup
@@ -56,7 +57,7 @@ struct EdgeConsts {                       // per-layer vectors, passed by value 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ EdgeConsts cst,
                      const float* __restrict__ proj, const double* __restrict__ x_in, const double* __restrict__ x_orig,
-                     float* __restrict__ aggr, double* __restrict__ x_out, int* __restrict__ status, int tn) {
+                     float* __restrict__ aggr, double* __restrict__ x_out, int* __restrict__ status, int tn, unsigned stagger_ns) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
   const int tid = threadIdx.x, wg = tid >> 8, q = tid & 255, half = q >> 7, r = q & 127, warp = tid >> 5;
@@ -92,7 +93,7 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
   const unsigned tmem_wg = tmem_base_u + (unsigned)wg_u * 256;                   // lane 0 (MMA issuer's view)
   const unsigned tmem = tmem_wg + ((unsigned)((warp & 3) * 32) << 16);           // my lane quarter
   const unsigned d_col = tmem + half * 32;                                         // my half of D (64 columns)
-  const unsigned a_col = tmem + 64;                                                // A: 3 splits x 32 columns
+  const unsigned a_col = tmem + 128;                                               // A: 3 splits x 32 columns (D: 0..127)
   mbar_wait(&S.w_bar, 0);
   unsigned mma_phase = 0, he_phase = 0;
   const unsigned w_saddr = smem_u32(S.w);
@@ -152,6 +153,9 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     cp_async_commit();
   };
 
+  // The two tile groups run identical code: started together they stay in phase and collide on the tensor pipe, the
+  // LSU and the barriers instead of filling each other's waits.  Hold group 1 back by about half a tile.
+  if (wg == 1 && stagger_ns > 0) __nanosleep(stagger_ns);
   int tile = blockIdx.x * 2 + wg;
   const int tstride = gridDim.x * 2;
   int buf = 0;
@@ -240,7 +244,7 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     if (issuer_warp) {
       tc_fence_after();
       if (elect_one()) {
-        issue_gemm(tmem_wg, tmem_wg + 64, 32, w_saddr, TC_W1_SPLIT, 3);
+        issue_gemm(tmem_wg, tmem_wg + 128, 32, w_saddr, TC_W1_SPLIT, 3);
         umma_commit(&S.mma_bar[wg_u]);
       }
       __syncwarp();
@@ -292,11 +296,24 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     }
     tc_fence_before();
     wg_barrier(wg);  // A operand complete; everyone is done with the Psrc staging (it becomes the msg tile)
-    // ---- GEMM2: edge_mlp.4 -> msg ---------------------------------------------------------------------
+    // ---- GEMM2+3 as ONE N=128 GEMM on the same A operand ----------------------------------------------------
+    // msg = W2 a1 + b2 (edge_mlp.4) and the coordinate MLP's hidden pre-activation W3 msg + b3 =
+    // (W3 W2) a1 + (W3 b2 + b3) are both linear in a1: the stacked panel [W2 ; W3 W2] gives them in one pass,
+    // which removes a bf16x3 split of msg, a TMEM store, an MMA phase and two barriers per tile.
     if (issuer_warp) {
       tc_fence_after();
       if (elect_one()) {
-        issue_gemm(tmem_wg, tmem_wg + 64, 32, w_saddr + TC_W2_BASE, TC_W23_SPLIT, 4);
+        const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};
+        const unsigned idesc = umma_idesc(128, 0);
+        unsigned accum = 0;
+#pragma unroll
+        for (int pr = 0; pr < 6; ++pr)
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            umma_ts_i(tmem_wg, tmem_wg + 128 + pa[pr] * 32 + kb * 8,
+                      b_desc_ex(w_saddr + TC_W23_BASE + pb[pr] * TC_W23_SPLIT + kb * 4096, 2048, 128), idesc, accum);
+            accum = 1;
+          }
         umma_commit(&S.mma_bar[wg_u]);
       }
       __syncwarp();
@@ -306,28 +323,30 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     tc_fence_after();
     {
       float v[32];
-      tmem_ld32f(d_col, v);
+      tmem_ld32f(d_col, v);                       // msg half row
 #pragma unroll
       for (int c = 0; c < 32; ++c) v[c] += cst.b2[half * 32 + c];
       float4* ms = reinterpret_cast<float4*>(&W.stage[r * TC_LD + half * 32]);
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) ms[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
-      store_half_split3(a_col + half * 16, v);
+      tmem_ld32f(d_col + 64, v);                  // coordinate-MLP hidden half row
+      float ph4[4] = {0.f, 0.f, 0.f, 0.f};        // 4 independent chains; the two halves are combined in fp64
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        ph4[c & 3] = fmaf(lrelu(v[c] + cst.b3[half * 32 + c], slope), cst.w4[half * 32 + c], ph4[c & 3]);  // :153-159
+      W.red[r * 2 + half] = ((double)ph4[0] + (double)ph4[1]) + ((double)ph4[2] + (double)ph4[3]);
     }
     cp_async_wait<0>();  // next tile's indices have landed (issued behind GEMM1)
     tc_fence_before();
     wg_barrier(wg);
     if (has_next) prefetch_x(buf ^ 1, nen);  // its x[src], x[dst]: xs of this tile was consumed in S1
-    // ---- GEMM3: coors_mlp.0 ; mean aggregation of msg overlaps the MMAs ---------------------------------
-    if (issuer_warp) {
-      tc_fence_after();
-      if (elect_one()) {
-        issue_gemm(tmem_wg, tmem_wg + 64, 32, w_saddr + TC_W3_BASE, TC_W23_SPLIT, 4);
-        umma_commit(&S.mma_bar[wg_u]);
-      }
-      __syncwarp();
+    if (half == 1) {
+      const double ph = W.red[r * 2] + W.red[r * 2 + 1] + (double)p.b_coor2;
+      W.xm[r * 3 + 0] = rx * ph;  // x_rel * phi :264
+      W.xm[r * 3 + 1] = ry * ph;
+      W.xm[r * 3 + 2] = rz * ph;
     }
-    for (int o = q; o < nn * 64; o += 256) {  // :280-283
+    for (int o = q; o < nn * 64; o += 256) {  // mean aggregation of msg :280-283
       const int nd = o >> 6, c = o & 63;
       const int rs = W.rp[buf][nd] - e0, re = W.rp[buf][nd + 1] - e0;
       const float* col = W.stage + c;
@@ -344,26 +363,6 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
       if (rr + 2 < re) s2 += col[(rr + 2) * TC_LD];
       const int deg = re - rs;
       aggr[(long)(n0 + nd) * 64 + c] = deg > 0 ? ((s0 + s1) + (s2 + s3)) / (float)deg : 0.f;
-    }
-    mbar_wait(&S.mma_bar[wg], mma_phase);
-    mma_phase ^= 1;
-    tc_fence_after();
-    {
-      float v[32];
-      tmem_ld32f(d_col, v);
-      float ph4[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent chains; the two halves are combined in fp64
-#pragma unroll
-      for (int c = 0; c < 32; ++c)
-        ph4[c & 3] = fmaf(lrelu(v[c] + cst.b3[half * 32 + c], slope), cst.w4[half * 32 + c], ph4[c & 3]);  // :153-159
-      W.red[r * 2 + half] = ((double)ph4[0] + (double)ph4[1]) + ((double)ph4[2] + (double)ph4[3]);
-    }
-    tc_fence_before();
-    wg_barrier(wg);
-    if (half == 1) {
-      const double ph = W.red[r * 2] + W.red[r * 2 + 1] + (double)p.b_coor2;
-      W.xm[r * 3 + 0] = rx * ph;  // x_rel * phi :264
-      W.xm[r * 3 + 1] = ry * ph;
-      W.xm[r * 3 + 2] = rz * ph;
     }
     wg_barrier(wg);
     for (int o = q; o < nn * 3; o += 256) {  // :274-277, 286-292
@@ -405,8 +404,9 @@ extern "C" int eqd_edge_stage(const eqd_graph* g, const eqd_layer_params* p, con
   cudaFuncSetAttribute(eqd::edge_stage_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int grid = (ntiles + 1) / 2;
   if (grid > 148) grid = 148;
+  static const unsigned stagger_ns = getenv("EQD_EDGE_STAGGER_NS") ? (unsigned)atoi(getenv("EQD_EDGE_STAGGER_NS")) : 0u;
   eqd::edge_stage_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(*g, *p, cst, proj, x_in, x_orig, aggr, x_out,
-                                                                             status, tn);
+                                                                             status, tn, stagger_ns);
   EQD_CUDA_LAUNCH_CHECK();
   return EQD_OK;
 }

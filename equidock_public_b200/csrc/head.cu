@@ -66,9 +66,57 @@ __device__ __forceinline__ double warp_max_d(double v) {
   return v;
 }
 
+// ---- batched head algebra: the 1.6 MB of read-out weights are streamed ONCE per batch, not once per protein ---
+// qbar[s][64] = mean over segment s of LeakyReLU(W_m h + b_m)   (from the per-tile partial sums)
+__global__ void head_qbar_kernel(eqd_graph g, const float* __restrict__ part, const int* __restrict__ tile_ptr,
+                                 double* __restrict__ qbar) {
+  int s = blockIdx.x, c = threadIdx.x;  // 64 threads
+  double acc = 0.0;
+  for (int t = tile_ptr[s]; t < tile_ptr[s + 1]; ++t) acc += (double)part[(long)t * 64 + c];
+  int n = g.seg_ptr[s + 1] - g.seg_ptr[s];
+  qbar[(long)s * 64 + c] = n > 0 ? acc / (double)n : 0.0;
+}
+// qk[s][row] = <W_query[row], qbar[s]>, row < 3200.  CTA = 32 rows of W_query (smem) x all segments.
+__global__ void __launch_bounds__(256) head_qk_kernel(int nseg, eqd_head_params hp, const double* __restrict__ qbar,
+                                                      double* __restrict__ qk) {
+  __shared__ float w[32][65];
+  const int row0 = blockIdx.x * 32, tid = threadIdx.x;
+  for (int i = tid; i < 32 * 64; i += 256) w[i >> 6][i & 63] = hp.w_query[(long)(row0 + (i >> 6)) * 64 + (i & 63)];
+  __syncthreads();
+  const int rl = tid & 31, sl = tid >> 5;   // 32 rows x 8 segments per pass
+  for (int s = sl; s < nseg; s += 8) {
+    const double* qv = qbar + (long)s * 64;
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+    for (int d = 0; d < 64; d += 2) {
+      a0 = fma((double)w[rl][d], qv[d], a0);
+      a1 = fma((double)w[rl][d + 1], qv[d + 1], a1);
+    }
+    qk[(long)s * (EQD_HEADS * 64) + row0 + rl] = a0 + a1;
+  }
+}
+// u[s][k][d] = sum_d' W_key[k*64+d'][d] * qk[partner(s)][k*64+d'] / sqrt(64).  CTA = one head k (W_key block in smem).
+__global__ void __launch_bounds__(256) head_u_kernel(int n_pairs, eqd_head_params hp, const double* __restrict__ qk,
+                                                     double* __restrict__ u) {
+  __shared__ float w[64][64];
+  const int k = blockIdx.x, tid = threadIdx.x, nseg = 2 * n_pairs;
+  for (int i = tid; i < 64 * 64; i += 256) w[i >> 6][i & 63] = hp.w_key[(long)k * 4096 + i];
+  __syncthreads();
+  const int d = tid & 63;
+  for (int s = blockIdx.y * 4 + (tid >> 6); s < nseg; s += gridDim.y * 4) {
+    const int ps = s < n_pairs ? s + n_pairs : s - n_pairs;   // the query comes from the partner protein (:544, :555)
+    const double* q = qk + (long)ps * (EQD_HEADS * 64) + k * 64;
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+    for (int dd = 0; dd < 64; dd += 2) {
+      a0 = fma((double)w[dd][d], q[dd], a0);
+      a1 = fma((double)w[dd + 1][d], q[dd + 1], a1);
+    }
+    u[((long)s * EQD_HEADS + k) * 64 + d] = (a0 + a1) * 0.125;  // / math.sqrt(d), d = 64 (:545)
+  }
+}
+
 struct KeypSmem {
-  double qbar[64];
-  double qk[EQD_HEADS * 64];
   double u[EQD_HEADS * HEAD_ULD];
   double state[EQD_HEADS * 5];  // running (max, sum, y.x, y.y, y.z) per head
   float hc[HEAD_JC * HEAD_HLD];
@@ -77,47 +125,21 @@ struct KeypSmem {
 
 // One CTA per segment s (a protein): keypoints Y_s[50][3] (:542-560).
 __global__ void __launch_bounds__(HEAD_THREADS)
-keypoints_kernel(eqd_graph g, eqd_head_params hp, const float* __restrict__ h, const double* __restrict__ x,
-                 const float* __restrict__ part, const int* __restrict__ tile_ptr /* [2B+1] first tile of each segment */,
-                 double* __restrict__ keypts) {
+keypoints_kernel(eqd_graph g, const float* __restrict__ h, const double* __restrict__ x,
+                 const double* __restrict__ u_all /* [2B][50][64] */, double* __restrict__ keypts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KeypSmem& s = *reinterpret_cast<KeypSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int B = g.n_pairs;
   const int seg = blockIdx.x;
-  const int pseg = seg < B ? seg + B : seg - B;
   const int i0 = g.seg_ptr[seg], i1 = g.seg_ptr[seg + 1];
 
-  // query = mean over the PARTNER protein's nodes (:544, :555)
-  if (tid < 64) {
-    double acc = 0.0;
-    for (int t = tile_ptr[pseg]; t < tile_ptr[pseg + 1]; ++t) acc += (double)part[(long)t * 64 + tid];
-    int np = g.seg_ptr[pseg + 1] - g.seg_ptr[pseg];
-    s.qbar[tid] = np > 0 ? acc / (double)np : 0.0;
-  }
+  for (int o = tid; o < EQD_HEADS * 64; o += HEAD_THREADS) s.u[(o >> 6) * HEAD_ULD + (o & 63)] = u_all[(long)seg * (EQD_HEADS * 64) + o];
   if (tid < EQD_HEADS) {
     s.state[tid * 5 + 0] = -INFINITY;
     s.state[tid * 5 + 1] = 0.0;
     s.state[tid * 5 + 2] = 0.0;
     s.state[tid * 5 + 3] = 0.0;
     s.state[tid * 5 + 4] = 0.0;
-  }
-  __syncthreads();
-  // qk = W_query qbar   (3200 dot products of length 64; one warp per row, coalesced)
-  for (int r = warp; r < EQD_HEADS * 64; r += HEAD_THREADS / 32) {
-    const float* wr = hp.w_query + (long)r * 64;
-    double v = (double)wr[lane] * s.qbar[lane] + (double)wr[lane + 32] * s.qbar[lane + 32];
-    v = warp_sum_d(v);
-    if (lane == 0) s.qk[r] = v;
-  }
-  __syncthreads();
-  // u[k][d] = sum_d' W_key[k*64+d'][d] * qk[k*64+d'] / sqrt(64)
-  for (int o = tid; o < EQD_HEADS * 64; o += HEAD_THREADS) {
-    int k = o >> 6, d = o & 63;
-    const float* wk = hp.w_key + (long)k * 64 * 64 + d;
-    double v = 0.0;
-    for (int dd = 0; dd < 64; ++dd) v += (double)wk[dd * 64] * s.qk[k * 64 + dd];
-    s.u[k * HEAD_ULD + d] = v * 0.125;  // / math.sqrt(d), d = 64 (:545)
   }
   __syncthreads();
 
@@ -374,10 +396,15 @@ static inline size_t eqd_align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 extern "C" int eqd_abi_version(void) { return EQD_ABI_VERSION; }
 
+static inline size_t ws_part_bytes(int32_t n_node_tiles) { return eqd_align256((size_t)(n_node_tiles > 0 ? n_node_tiles : 1) * 64 * sizeof(float)); }
+static inline size_t ws_tile_ptr_bytes(int32_t n_pairs) { return eqd_align256((size_t)(2 * (n_pairs > 0 ? n_pairs : 0) + 1) * sizeof(int)); }
+static inline size_t ws_qbar_bytes(int32_t n_pairs) { return eqd_align256((size_t)2 * (n_pairs > 0 ? n_pairs : 1) * 64 * sizeof(double)); }
+static inline size_t ws_qk_bytes(int32_t n_pairs) { return eqd_align256((size_t)2 * (n_pairs > 0 ? n_pairs : 1) * EQD_HEADS * 64 * sizeof(double)); }
+
 extern "C" size_t eqd_workspace_bytes(int32_t n_nodes, int32_t n_node_tiles, int32_t n_pairs) {
   (void)n_nodes;
-  return eqd_align256((size_t)(n_node_tiles > 0 ? n_node_tiles : 1) * 64 * sizeof(float)) +
-         eqd_align256((size_t)(2 * (n_pairs > 0 ? n_pairs : 0) + 1) * sizeof(int));
+  // per-tile partial sums | first tile of each segment | qbar[2B][64] | qk[2B][3200] | u[2B][50][64]   (fp64 from qbar on)
+  return ws_part_bytes(n_node_tiles) + ws_tile_ptr_bytes(n_pairs) + ws_qbar_bytes(n_pairs) + 2 * ws_qk_bytes(n_pairs);
 }
 
 extern "C" int eqd_keypoints(const eqd_graph* g, const eqd_head_params* hp, const float* h, const double* x,
@@ -387,9 +414,13 @@ extern "C" int eqd_keypoints(const eqd_graph* g, const eqd_head_params* hp, cons
   if (workspace_bytes < eqd_workspace_bytes(g->n_nodes, g->n_node_tiles, g->n_pairs)) return EQD_ERR_WORKSPACE;
   if (g->n_pairs <= 0) return EQD_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  float* part = reinterpret_cast<float*>(workspace);
-  int* tile_ptr = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(workspace) +
-                                         eqd_align256((size_t)(g->n_node_tiles > 0 ? g->n_node_tiles : 1) * 64 * sizeof(float)));
+  unsigned char* wsb = reinterpret_cast<unsigned char*>(workspace);
+  float* part = reinterpret_cast<float*>(wsb);
+  int* tile_ptr = reinterpret_cast<int*>(wsb + ws_part_bytes(g->n_node_tiles));
+  double* qbar = reinterpret_cast<double*>(wsb + ws_part_bytes(g->n_node_tiles) + ws_tile_ptr_bytes(g->n_pairs));
+  double* qk = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(qbar) + ws_qbar_bytes(g->n_pairs));
+  double* u = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(qk) + ws_qk_bytes(g->n_pairs));
+  const int nseg = 2 * g->n_pairs;
   {
     size_t smem = (size_t)(EQD_TM * 68 + 2 * EQD_WCHUNK * EQD_WLD) * sizeof(float);
     cudaFuncSetAttribute(eqd::head_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -398,14 +429,21 @@ extern "C" int eqd_keypoints(const eqd_graph* g, const eqd_head_params* hp, cons
     EQD_CUDA_LAUNCH_CHECK();
   }
   {
-    int nseg1 = 2 * g->n_pairs + 1;
-    eqd::tile_ptr_kernel<<<(nseg1 + 127) / 128, 128, 0, st>>>(*g, tile_ptr);
+    eqd::tile_ptr_kernel<<<(nseg + 1 + 127) / 128, 128, 0, st>>>(*g, tile_ptr);
+    EQD_CUDA_LAUNCH_CHECK();
+    eqd::head_qbar_kernel<<<nseg, 64, 0, st>>>(*g, part, tile_ptr, qbar);
+    EQD_CUDA_LAUNCH_CHECK();
+    eqd::head_qk_kernel<<<EQD_HEADS * 64 / 32, 256, 0, st>>>(nseg, *hp, qbar, qk);
+    EQD_CUDA_LAUNCH_CHECK();
+    int gy = (nseg + 3) / 4;
+    if (gy > 8) gy = 8;
+    eqd::head_u_kernel<<<dim3(EQD_HEADS, gy), 256, 0, st>>>(g->n_pairs, *hp, qk, u);
     EQD_CUDA_LAUNCH_CHECK();
   }
   {
     size_t smem = sizeof(eqd::KeypSmem);
     cudaFuncSetAttribute(eqd::keypoints_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    eqd::keypoints_kernel<<<2 * g->n_pairs, HEAD_THREADS, smem, st>>>(*g, *hp, h, x, part, tile_ptr, keypts);
+    eqd::keypoints_kernel<<<2 * g->n_pairs, HEAD_THREADS, smem, st>>>(*g, h, x, u, keypts);
     EQD_CUDA_LAUNCH_CHECK();
   }
   {

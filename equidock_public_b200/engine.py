@@ -74,11 +74,15 @@ class PackedLayer:
         self.dh, self.dhp = dh, dhp
         w1e = z(64, 48)
         w1e[:, :n_e] = w1[:, 2 * dh:]
-        w_edge_tc = torch.cat([umma_bf16x3(w1e), umma_bf16x3(f('edge_mlp.4.weight')),
-                               umma_bf16x3(f('coors_mlp.0.weight'))]).contiguous()
+        # coors_mlp.0 applied to msg = W2 a1 + b2 is linear in a1: (W3 W2) a1 + (W3 b2 + b3); the tensor-core edge stage
+        # evaluates [W2 ; W3 W2] as one N=128 panel on the same A operand (folded in fp64, stored fp32 -> bf16x3)
+        w2d, w3d = f('edge_mlp.4.weight').double(), f('coors_mlp.0.weight').double()
+        w32 = (w3d @ w2d).float()
+        b32 = (w3d @ f('edge_mlp.4.bias').double() + f('coors_mlp.0.bias').double()).float()
+        w_edge_tc = torch.cat([umma_bf16x3(w1e), umma_bf16x3(torch.cat([f('edge_mlp.4.weight'), w32]))]).contiguous()
         assert w_edge_tc.numel() * 2 == 67584
         self.edge_consts_host = torch.stack([f('edge_mlp.3.weight'), f('edge_mlp.3.bias'), f('edge_mlp.4.bias'),
-                                             f('coors_mlp.0.bias'), f('coors_mlp.4.weight').reshape(-1)]).cpu().contiguous()
+                                             b32, f('coors_mlp.4.weight').reshape(-1)]).cpu().contiguous()
         tc = {}
         self.node_consts_host = self.proj_bias_host = None
         if dh == nat.HID:  # tensor-core node stage panels (64-wide layers)
@@ -209,8 +213,8 @@ class IEGMNEngine:
     def launches_per_forward(n_layers: int) -> int:
         """Kernels of csrc/ launched by one forward: embed, project (layer 0), per layer edge stage + node stage
         (layer 0: fp32 node kernel + K/V blocks; 64-wide layers: attention, node MLP, next projections),
-        then head_mean, tile_ptr, keypoints, keypoint_cov, kabsch_apply."""
-        n = 2 + 5
+        then head_mean, tile_ptr, head_qbar, head_qk, head_u, keypoints, keypoint_cov, kabsch_apply."""
+        n = 2 + 8
         for li in range(n_layers):
             last = li == n_layers - 1
             n += 1 + ((1 + (0 if last else 1)) if li == 0 else (2 + (0 if last else 1)))
@@ -295,8 +299,15 @@ class IEGMNEngine:
             g, nat.ptr(cov), nat.ptr(ymean), nat.ptr(x_l), nat.ptr(mask), nat.ptr(rot), nat.ptr(trans),
             nat.ptr(lig_out), nat.ptr(sing), nat.ptr(status), st), 'eqd_kabsch_apply')
         kab(None)
+        # status words -> pinned host memory, asynchronously; resolve_status() waits on the event only, so a caller
+        # may launch the next forward before looking at this one's flags (bench.py keeps two steps in flight)
+        status_host = torch.empty(B + 2, dtype=torch.int32, pin_memory=True)
+        status_host.copy_(torch.cat([status, plan.unsorted.to(torch.int32).reshape(1)]), non_blocking=True)
+        status_event = torch.cuda.Event()
+        status_event.record()
         out = {'ligand_coors': lig_out, 'keypts': keyp, 'rotation': rot, 'translation': trans, 'h': h_fin,
-               'x64': x_fin, 'cov': cov, 'sing': sing, 'status': status, 'unsorted': plan.unsorted, 'kabsch': kab}
+               'x64': x_fin, 'cov': cov, 'sing': sing, 'status': status, 'unsorted': plan.unsorted, 'kabsch': kab,
+               'status_host': status_host, 'status_event': status_event}
         if check_status:
             self.resolve_status(plan, out, kab, log)
         return out
@@ -304,7 +315,8 @@ class IEGMNEngine:
     def resolve_status(self, plan: GraphPlan, out, kab, log=None):
         """The ONE host sync of a forward: reads the status words and replays the reference's
         host-side control flow for flagged pairs (rigid_docking_model.py:570-584)."""
-        st_host = torch.cat([out['status'], out['unsorted'].to(torch.int32).reshape(1)]).cpu()
+        out['status_event'].synchronize()
+        st_host = out['status_host']
         if int(st_host[-1]) != 0:
             raise UnsortedEdges()
         if int(st_host[plan.n_pairs]) & nat.STATUS_DEGREE_OVERFLOW:

@@ -310,8 +310,9 @@ class IEGMN(nn.Module):
             self._head_key = key
         return self._head
 
-    def run_engine(self, batch_hetero_graph):
-        """The whole hot path on the device; returns the engine's raw output dict."""
+    def run_engine(self, batch_hetero_graph, check_status=True):
+        """The whole hot path on the device; returns the engine's raw output dict.  With ``check_status=False`` the
+        per-pair status words are left pending (``resolve(out)`` finishes the call)."""
         emb = self.residue_emb_layer.weight
         dev = emb.device
         for lay in self.iegmn_layers:
@@ -322,20 +323,31 @@ class IEGMN(nn.Module):
         nl, nr = batch_hetero_graph.nodes[LIGAND].data, batch_hetero_graph.nodes[RECEPTOR].data
         plan = _plan_for(batch_hetero_graph, dev, self.graph_max_neighbor)
         emb32 = emb.detach().to(torch.float32).contiguous()
-        call = lambda p: eng.forward(p, emb32, layers, head, nl['res_feat'], nr['res_feat'], nl['mu_r_norm'],
-                                     nr['mu_r_norm'], nl['new_x'], nr['x'], True, self.log)
+        call = lambda p, chk: eng.forward(p, emb32, layers, head, nl['res_feat'], nr['res_feat'], nl['mu_r_norm'],
+                                          nr['mu_r_norm'], nl['new_x'], nr['x'], chk, self.log)
         try:
-            out = call(plan)
+            out = call(plan, check_status)
         except UnsortedEdges:
             plan = _sorted_plan(batch_hetero_graph, dev, self.graph_max_neighbor)
-            out = call(plan)
-        out['plan'] = plan
+            out = call(plan, True)
+        out['plan'], out['engine'], out['graph'] = plan, eng, batch_hetero_graph
         return out
+
+    def resolve(self, out):
+        """Finishes a ``run_engine(..., check_status=False)`` call: waits for its status words and replays the
+        reference's host-side control flow for flagged pairs (:570-584).  Unsorted edge lists are re-run sorted."""
+        try:
+            out['engine'].resolve_status(out['plan'], out, out['kabsch'], self.log)
+            return out
+        except UnsortedEdges:
+            return self.run_engine(out['graph'], True)
 
     def forward(self, batch_hetero_graph, epoch):
         """Returns ``[T list, b list, Y_ligand list, Y_receptor list]`` like the reference (:602) and
         writes ``x_iegmn_out`` / ``hv_iegmn_out`` into the graph (:507-510)."""
-        out = self.run_engine(batch_hetero_graph)
+        return self.package(self.run_engine(batch_hetero_graph), batch_hetero_graph)
+
+    def package(self, out, batch_hetero_graph):
         plan = out['plan']
         B, N_l = plan.n_pairs, plan.N_l
         dt = batch_hetero_graph.nodes[LIGAND].data['new_x'].dtype
@@ -371,8 +383,21 @@ class Rigid_Body_Docking_Net(nn.Module):
             else:
                 torch.nn.init.zeros_(p)
 
+    def forward_async(self, batch_hetero_graph, epoch=0):
+        """Launches the whole forward without waiting for its status words; ``.result()`` of the returned handle
+        completes it and returns the reference's 5-tuple.  Lets a serving loop keep several batches in flight."""
+        net, raw = self, self.iegmn_original.run_engine(batch_hetero_graph, check_status=False)
+
+        class Pending:
+            def result(self_inner):
+                out = net.iegmn_original.resolve(raw)
+                return net._assemble(net.iegmn_original.package(out, batch_hetero_graph))
+        return Pending()
+
     def forward(self, batch_hetero_graph, epoch):
-        outputs = self.iegmn_original(batch_hetero_graph, epoch)
+        return self._assemble(self.iegmn_original(batch_hetero_graph, epoch))
+
+    def _assemble(self, outputs):
         assert len(outputs) == 4
         raw = self.iegmn_original.last_outputs
         plan = raw['plan']

@@ -100,11 +100,13 @@ typedef struct eqd_layer_params {
   /* tensor-core edge stage (tcgen05): the three edge-side weight matrices, each split into 3 bf16 terms
    * (w ~ w0+w1+w2, round-to-nearest) and stored in the UMMA canonical K-major no-swizzle layout
    *   element (n,k) of split s at  base + s*split_bytes + (k/8)*1024 + (n/8)*128 + (n%8)*16 + (k%8)*2
-   * GEMM1 = edge_mlp.0.weight[:, 2dh:] (K 42 -> 48, base 0, split 6144 B), GEMM2 = edge_mlp.4.weight
-   * (base 18432, split 8192 B), GEMM3 = coors_mlp.0.weight (base 43008, split 8192 B); 67584 B, 16B-aligned. */
+   * GEMM1 = edge_mlp.0.weight[:, 2dh:] ([64][48], K 42 -> 48, base 0, split 6144 B); GEMM2+3 = the stacked
+   * [128][64] panel [edge_mlp.4.weight ; coors_mlp.0.weight @ edge_mlp.4.weight] (base 18432, split 16384 B,
+   * k-chunk stride 2048 B): msg and the coordinate MLP's hidden layer are both linear in the LayerNorm output.
+   * 67584 B, 16B-aligned. */
   const void* w_edge_tc;
-  /* HOST pointer to [5][64] floats: edge_ln_g, edge_ln_b, b_edge2, b_coor1, w_coor2 (copied into the kernel's
-   * constant parameter space at launch). */
+  /* HOST pointer to [5][64] floats: edge_ln_g, edge_ln_b, b_edge2, (coors_mlp.0.weight @ b_edge2 + b_coor1),
+   * w_coor2 (copied into the kernel's constant parameter space at launch). */
   const float* edge_consts_host;
   /* tensor-core node stage (dh == 64 layers only; NULL for the 69-wide layer 0). Same bf16x3 UMMA panels:
    *   w_node_tc : node_mlp.0.weight padded to [64][272] (K order h | aggr | mu | h0(69) | 0) at base 0, split

@@ -163,4 +163,4 @@ def test_unsupported_configurations_raise():
 
 
 def test_launch_accounting():
-    assert IEGMNEngine.launches_per_forward(8) == 37 and IEGMNEngine.launches_per_forward(5) == 25
+    assert IEGMNEngine.launches_per_forward(8) == 40 and IEGMNEngine.launches_per_forward(5) == 28
