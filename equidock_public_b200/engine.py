@@ -155,9 +155,9 @@ class GraphPlan:
         # read together with the per-pair status (one sync per forward).
         d64 = self.edge_dst.long()
         self.unsorted = ((d64[1:] < d64[:-1]).any() if self.E > 1 else torch.zeros((), dtype=torch.bool, device=device))
-        deg = torch.bincount(d64, minlength=self.N)
-        self.row_ptr = torch.zeros(self.N + 1, **i32)
-        self.row_ptr[1:] = torch.cumsum(deg, 0).to(torch.int32)
+        # row_ptr[n] = first edge whose destination is >= n.  searchsorted on the (sorted) destination list needs no
+        # host sync -- torch.bincount would block the CPU on the previous batch and break the copy/compute overlap.
+        self.row_ptr = torch.searchsorted(self.edge_dst, torch.arange(self.N + 1, **i32), out_int32=True).contiguous()
         self.he_l = he_l.to(device=device, dtype=torch.float32).contiguous()
         self.he_r = he_r.to(device=device, dtype=torch.float32).contiguous()
         assert self.he_l.shape == (self.E_l, nat.EDGE_FEATS) and self.he_r.shape == (self.E_r, nat.EDGE_FEATS)
@@ -204,6 +204,21 @@ def _sorted_copy(plan_args):
         out.append((s[perm], d[perm], he[perm]))
     (sl, dl, hl), (sr, dr, hr) = out
     return n_l, n_r, sl, dl, sr, dr, hl, hr, device, mid
+
+
+_STATUS_RING = {'bufs': [], 'next': 0}
+
+
+def _pinned_status(n: int) -> torch.Tensor:
+    """A pinned int32 buffer from a small ring (8 deep: more than the number of forwards ever in flight).  Allocating
+    page-locked memory per call (cudaHostAlloc) stalls the CPU for tens of milliseconds every few steps."""
+    ring = _STATUS_RING
+    if not ring['bufs'] or ring['bufs'][0].numel() < n:
+        ring['bufs'] = [torch.empty(max(n, 1024), dtype=torch.int32, pin_memory=True) for _ in range(8)]
+        ring['next'] = 0
+    buf = ring['bufs'][ring['next'] % 8]
+    ring['next'] += 1
+    return buf[:n]
 
 
 class IEGMNEngine:
@@ -301,7 +316,7 @@ class IEGMNEngine:
         kab(None)
         # status words -> pinned host memory, asynchronously; resolve_status() waits on the event only, so a caller
         # may launch the next forward before looking at this one's flags (bench.py keeps two steps in flight)
-        status_host = torch.empty(B + 2, dtype=torch.int32, pin_memory=True)
+        status_host = _pinned_status(B + 2)
         status_host.copy_(torch.cat([status, plan.unsorted.to(torch.int32).reshape(1)]), non_blocking=True)
         status_event = torch.cuda.Event()
         status_event.record()
