@@ -187,6 +187,7 @@ extern "C" int eqd_edge_stage_ffma(const eqd_graph* g, const eqd_layer_params* p
                               const double* x_orig, float* aggr, double* x_out, int32_t* status, void* stream) {
   if (!g || !p || !proj || !x_in || !x_orig || !aggr || !x_out || !status) return EQD_ERR_BAD_ARG;
   if (g->max_in_degree < 1 || g->max_in_degree > EQD_TM) return EQD_ERR_UNSUPPORTED;
+  if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)
   if (g->n_nodes <= 0) return EQD_OK;
   int tn = EQD_TM / g->max_in_degree;
   if (tn > EQD_TM) tn = EQD_TM;

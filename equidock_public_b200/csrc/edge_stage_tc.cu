@@ -189,19 +189,6 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     wg_barrier(wg);
     const bool valid = r < ne;
     const int dn = valid ? W.dst[buf][r] : 0;
-    // gathers of the node projections into smem (coalesced 16B chunks, 16 lanes per row)
-#pragma unroll
-    for (int idx = q; idx < EQD_TM * 16; idx += 256) {
-      int row = idx >> 4, c4 = idx & 15;
-      bool ok = row < ne;
-      int s_row = ok ? W.src[buf][row] : 0;
-      cp_async16(&W.stage[row * TC_LD + c4 * 4], proj + (long)s_row * pw + c4 * 4, ok);
-    }
-    for (int idx = q; idx < nn * 16; idx += 256) {
-      int row = idx >> 4, c4 = idx & 15;
-      cp_async16(&W.pdst[row * TC_LD + c4 * 4], proj + (long)(n0 + row) * pw + 64 + c4 * 4, true);
-    }
-    cp_async_commit();
     double rx = 0.0, ry = 0.0, rz = 0.0;
     {
       float a1v[24];  // half 0: he[0..23];  half 1: he[24..26], 15 RBFs, 6 zeros
@@ -220,12 +207,15 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
 #pragma unroll
         for (int k = 0; k < 3; ++k) a1v[k] = valid ? hrow[24 + k] : 0.f;
         const float nd2 = -(float)(rx * rx + ry * ry + rz * rz);  // :208-209
-        // exp(-d^2 / 1.5^q) :210 -- correctly rounded reciprocals of sigma (1.5^q is exact in fp32)
+        // exp(-d^2 / 1.5^q) :210 as ex2.approx(-d^2 * log2(e)/1.5^q): 2 instructions per RBF instead of ~20; the
+        // features are <= 1 and the absolute error (<= 2e-7: 2^-22 of ex2 + the rounded scale factor) is below the
+        // bf16x3 operand resolution of the GEMM they feed
         constexpr double kS[EQD_N_RBF] = {1.0, 1.5, 2.25, 3.375, 5.0625, 7.59375, 11.390625, 17.0859375, 25.62890625,
                                           38.443359375, 57.6650390625, 86.49755859375, 129.746337890625,
                                           194.6195068359375, 291.92926025390625};
 #pragma unroll
-        for (int j = 0; j < EQD_N_RBF; ++j) a1v[3 + j] = valid ? expf(nd2 * (float)(1.0 / kS[j])) : 0.f;
+        for (int j = 0; j < EQD_N_RBF; ++j)
+          a1v[3 + j] = valid ? exp2f(nd2 * (float)(1.4426950408889634 / kS[j])) : 0.f;
 #pragma unroll
         for (int k = 18; k < 24; ++k) a1v[k] = 0.f;
       }
@@ -249,6 +239,20 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
       }
       __syncwarp();
     }
+    // gathers of the node projections into smem (coalesced 16B chunks, 16 lanes per row): issued behind GEMM1,
+    // which they overlap -- they are first needed by epilogue 1
+#pragma unroll
+    for (int idx = q; idx < EQD_TM * 16; idx += 256) {
+      int row = idx >> 4, c4 = idx & 15;
+      bool ok = row < ne;
+      int s_row = ok ? W.src[buf][row] : 0;
+      cp_async16(&W.stage[row * TC_LD + c4 * 4], proj + (long)s_row * pw + c4 * 4, ok);
+    }
+    for (int idx = q; idx < nn * 16; idx += 256) {
+      int row = idx >> 4, c4 = idx & 15;
+      cp_async16(&W.pdst[row * TC_LD + c4 * 4], proj + (long)(n0 + row) * pw + 64 + c4 * 4, true);
+    }
+    cp_async_commit();
     // he staging and the other index buffer are free now: prefetch the next tile behind the MMAs
     if (has_next) prefetch(tile + tstride, buf ^ 1, e0n, nen, off_ln, n_ln, off_rn);
     mbar_wait(&S.mma_bar[wg], mma_phase);
@@ -346,23 +350,20 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
       W.xm[r * 3 + 1] = ry * ph;
       W.xm[r * 3 + 2] = rz * ph;
     }
-    for (int o = q; o < nn * 64; o += 256) {  // mean aggregation of msg :280-283
-      const int nd = o >> 6, c = o & 63;
-      const int rs = W.rp[buf][nd] - e0, re = W.rp[buf][nd + 1] - e0;
+    {  // mean aggregation of msg at the destination nodes (:280-283): 4 threads per channel, each a run of nodes
+      const int c = q & 63, part = q >> 6;
       const float* col = W.stage + c;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      int rr = rs;
-      for (; rr + 4 <= re; rr += 4) {  // 4 independent loads in flight
-        s0 += col[rr * TC_LD];
-        s1 += col[(rr + 1) * TC_LD];
-        s2 += col[(rr + 2) * TC_LD];
-        s3 += col[(rr + 3) * TC_LD];
+      for (int nd = (nn * part) >> 2, nd1 = (nn * (part + 1)) >> 2; nd < nd1; ++nd) {
+        const int rs = W.rp[buf][nd] - e0, re = W.rp[buf][nd + 1] - e0;
+        float s0 = 0.f, s1 = 0.f;
+        int rr = rs;
+        for (; rr + 1 < re; rr += 2) {
+          s0 += col[rr * TC_LD];
+          s1 += col[(rr + 1) * TC_LD];
+        }
+        if (rr < re) s0 += col[rr * TC_LD];
+        aggr[(long)(n0 + nd) * 64 + c] = re > rs ? (s0 + s1) / (float)(re - rs) : 0.f;
       }
-      if (rr < re) s0 += col[rr * TC_LD];
-      if (rr + 1 < re) s1 += col[(rr + 1) * TC_LD];
-      if (rr + 2 < re) s2 += col[(rr + 2) * TC_LD];
-      const int deg = re - rs;
-      aggr[(long)(n0 + nd) * 64 + c] = deg > 0 ? ((s0 + s1) + (s2 + s3)) / (float)deg : 0.f;
     }
     wg_barrier(wg);
     for (int o = q; o < nn * 3; o += 256) {  // :274-277, 286-292
@@ -391,6 +392,7 @@ extern "C" int eqd_edge_stage(const eqd_graph* g, const eqd_layer_params* p, con
   if (!g || !p || !proj || !x_in || !x_orig || !aggr || !x_out || !status) return EQD_ERR_BAD_ARG;
   if (!p->w_edge_tc || !p->edge_consts_host) return EQD_ERR_BAD_ARG;
   if (g->max_in_degree < 1 || g->max_in_degree > EQD_TM) return EQD_ERR_UNSUPPORTED;
+  if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)
   if ((reinterpret_cast<uintptr_t>(g->he_lig) | reinterpret_cast<uintptr_t>(g->he_rec) |
        reinterpret_cast<uintptr_t>(p->w_edge_tc)) & 15)
     return EQD_ERR_BAD_ARG;  // bulk copies need 16-byte aligned bases

@@ -80,6 +80,7 @@ extern "C" int eqd_project(const eqd_graph* g, const eqd_layer_params* p, const 
                            void* stream) {
   if (!g || !p || !h || !proj) return EQD_ERR_BAD_ARG;
   if (!((p->dh == 64 && p->dhp == 64) || (p->dh == 69 && p->dhp == 72))) return EQD_ERR_UNSUPPORTED;
+  if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)
   if (g->n_nodes <= 0) return EQD_OK;
   int ntiles = (g->n_nodes + EQD_TM - 1) / EQD_TM;
   size_t smem = (size_t)(EQD_TM * (p->dhp + 4) + 2 * EQD_WCHUNK * EQD_WLD) * sizeof(float);

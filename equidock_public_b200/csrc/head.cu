@@ -412,6 +412,7 @@ extern "C" int eqd_keypoints(const eqd_graph* g, const eqd_head_params* hp, cons
                              void* stream) {
   if (!g || !hp || !h || !x || !workspace || !keypts || !ymean || !cov) return EQD_ERR_BAD_ARG;
   if (workspace_bytes < eqd_workspace_bytes(g->n_nodes, g->n_node_tiles, g->n_pairs)) return EQD_ERR_WORKSPACE;
+  if (!(hp->leaky_slope >= 0.f && hp->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;
   if (g->n_pairs <= 0) return EQD_OK;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* wsb = reinterpret_cast<unsigned char*>(workspace);

@@ -204,6 +204,7 @@ extern "C" int eqd_node_mlp_tc(const eqd_graph* g, const eqd_layer_params* p, co
                                const float* mu, const float* h0, float* h_out, void* stream) {
   if (!g || !p || !h_in || !aggr || !mu || !h0 || !h_out) return EQD_ERR_BAD_ARG;
   if (p->dh != 64 || p->dhp != 64) return EQD_ERR_UNSUPPORTED;
+  if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)
   if (!p->w_node_tc || !p->node_consts_host || (reinterpret_cast<uintptr_t>(p->w_node_tc) & 15)) return EQD_ERR_BAD_ARG;
   if (g->n_nodes <= 0) return EQD_OK;
   eqd::NmConsts cst;

@@ -13,7 +13,9 @@ namespace eqd {
 template <bool EXTRA>
 struct NodeCfg {
   static constexpr int DHP = EXTRA ? 72 : 64;
-  static constexpr int LD = DHP + 4;  // smem row stride of tiles
+  // smem row stride of tiles: 68 for the 64-wide layers (conflict-free); the 72-wide layer 0 uses an unpadded 72
+  // (2-way conflicts on the K-chunk reads of Q K^T only) so that two CTAs fit per SM (110.6 KB each)
+  static constexpr int LD = EXTRA ? DHP : DHP + 4;
   static constexpr int KC = 64;       // keys per attention chunk
   static constexpr int BUF = EQD_TM * LD;
   static constexpr int KV = KC * LD + KC * DHP;  // K chunk (row stride LD) + V chunk (row stride DHP)
@@ -23,7 +25,7 @@ struct NodeCfg {
 };
 
 template <bool EXTRA>
-__global__ void __launch_bounds__(EQD_THREADS, EXTRA ? 1 : 2)
+__global__ void __launch_bounds__(EQD_THREADS, 2)
 node_stage_kernel(eqd_graph g, eqd_layer_params p, eqd_layer_params pn, int has_next, const float* __restrict__ h_in,
                   int ldh, const float* __restrict__ h0, const float* __restrict__ proj,
                   const float* __restrict__ aggr, float* __restrict__ h_out, float* __restrict__ proj_next) {
@@ -182,6 +184,7 @@ extern "C" int eqd_node_stage(const eqd_graph* g, const eqd_layer_params* p, con
   if (p_next && (!proj_next || p_next->dh != 64 || p_next->dhp != 64)) return EQD_ERR_BAD_ARG;
   const bool extra = (p->dh == 69 && p->dhp == 72);
   if (!extra && !(p->dh == 64 && p->dhp == 64)) return EQD_ERR_UNSUPPORTED;
+  if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)
   if (g->n_node_tiles <= 0) return EQD_OK;
   eqd_layer_params pn = p_next ? *p_next : *p;
   int has_next = p_next ? 1 : 0;
@@ -189,7 +192,7 @@ extern "C" int eqd_node_stage(const eqd_graph* g, const eqd_layer_params* p, con
   if (extra) {
     size_t smem = eqd::NodeCfg<true>::SMEM;
     cudaFuncSetAttribute(eqd::node_stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int grid = g->n_node_tiles < 148 ? g->n_node_tiles : 148;
+    int grid = g->n_node_tiles < 148 * 2 ? g->n_node_tiles : 148 * 2;
     eqd::node_stage_kernel<true><<<grid, EQD_THREADS, smem, st>>>(*g, *p, pn, has_next, h_in, ldh, h0, proj, aggr,
                                                                   h_out, proj_next);
   } else {

@@ -156,6 +156,7 @@ extern "C" int eqd_project_tc(const eqd_graph* g, const eqd_layer_params* p, con
                               void* stream) {
   if (!g || !p || !h || !proj) return EQD_ERR_BAD_ARG;
   if (p->dh != 64 || p->dhp != 64) return EQD_ERR_UNSUPPORTED;
+  if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)
   if (!p->w_proj_tc || !p->proj_bias_host || (reinterpret_cast<uintptr_t>(p->w_proj_tc) & 15)) return EQD_ERR_BAD_ARG;
   if (g->n_nodes <= 0) return EQD_OK;
   eqd::PjConsts cst;
