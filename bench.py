@@ -121,12 +121,29 @@ def make_workload(pairs_per_gpu: int, seed: int):
 
 
 def measured_peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s sustained, source).  The edge stage is timed inside a long step, so the sustained
+    tensor figure is the denominator."""
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.isfile(p):
         with open(p) as fh:
             d = json.load(fh)
-        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
-    return 6650.0, 'fallback (B200_PROFILING.md)'
+        return (float(d['hbm_gbs']), float(d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1380.0))),
+                'measured (MEASURED_PEAKS.json)')
+    return 6650.0, 1380.0, 'fallback (B200_PROFILING.md)'
+
+
+def edge_stage_algorithmic_flops(n_edges: int, dh: int = 64) -> float:
+    """fp32 FLOPs of ONE edge-stage launch in the reference formulation (SURVEY 8(d) per-layer edge terms, MAC = 2):
+    edge_mlp.0 on cat[h_src, h_dst, he, rbf] (2E(2 dh + 42) 64), edge_mlp.4 and coors_mlp.0 (2E 64 64 each),
+    coors_mlp.4 (2E 64)."""
+    return n_edges * (2.0 * (2 * dh + 42) * 64 + 2 * 2.0 * 64 * 64 + 2.0 * 64)
+
+
+# bf16 FLOPs the tensor-core edge stage really issues per edge: (K 48 x N 64 + K 64 x N 128) MACs x 6 split products
+EDGE_TC_BF16_FLOP_PER_EDGE = 2.0 * (48 * 64 + 64 * 128) * 6
+# dram__bytes_read.sum + dram__bytes_write.sum of one edge_stage_tc_kernel launch of this workload (ncu --set full,
+# profiles/r01_v2_edge_stage_tc_ncu_summary.txt): 176.5 MB + 19.3 MB
+EDGE_TC_NCU_TRAFFIC_BYTES = 195.8e6
 
 
 def effective_cores() -> int:
@@ -294,11 +311,12 @@ def run_engine(args, rank, local_rank, world):
 
     if rank != 0:
         return
-    hbm_peak, peak_src = measured_peaks()
+    hbm_peak, tc_peak, peak_src = measured_peaks()
     edge_ms = timer.mean_ms('edge_stage')
     node_ms = timer.mean_ms('node_stage')
     alg = edge_stage_algorithmic_bytes(n_nodes, n_edges)
     ach = alg / (edge_ms * 1e-3) / 1e9
+    alg_flops = edge_stage_algorithmic_flops(n_edges)
     step_ms = ms_total / args.steps
     sm_mhz = (clocks or {}).get('sm_mhz') or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
@@ -312,11 +330,18 @@ def run_engine(args, rank, local_rank, world):
         'e2e': {'value': e2e_val, 'unit': 'pairs/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes},
         'gpu_launches': IEGMNEngine.launches_per_forward(N_LAYERS) * args.steps,
         'clocks': clocks,
-        'roofline': {'kernel': 'edge_stage_kernel', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
-                     'frac': ach / hbm_peak, 'traffic': None, 'peak_source': peak_src,
-                     'algorithmic_bytes_per_launch': alg, 'launch_ms': edge_ms,
+        'roofline': {'kernel': 'edge_stage_tc_kernel', 'bound': 'tensor', 'achieved': alg_flops / (edge_ms * 1e-3) / 1e12,
+                     'peak': tc_peak, 'unit': 'TFLOP/s', 'frac': alg_flops / (edge_ms * 1e-3) / 1e12 / tc_peak,
+                     'traffic': EDGE_TC_NCU_TRAFFIC_BYTES if B == 256 else None, 'peak_source': peak_src + ', sustained bf16',
+                     'algorithmic_flops_per_launch': alg_flops, 'launch_ms': edge_ms,
+                     'issued_bf16_tflops': n_edges * EDGE_TC_BF16_FLOP_PER_EDGE / (edge_ms * 1e-3) / 1e12,
+                     'issued_bf16_frac': n_edges * EDGE_TC_BF16_FLOP_PER_EDGE / (edge_ms * 1e-3) / 1e12 / tc_peak,
+                     'hbm': {'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
+                             'algorithmic_bytes_per_launch': alg},
                      'share_of_step': timer.total_ms('edge_stage') / ms_total,
-                     'note': 'fp32-FFMA-bound by construction (AI ~290 FLOP/B, SURVEY 8d); HBM fraction reported as the north star asks'},
+                     'note': 'fp32-accurate GEMMs as 6 bf16 split products on tcgen05 (bf16x6): the tensor ceiling in '
+                             'algorithmic fp32 FLOPs is peak x 38272 / 135168 = 0.283 x peak; AI ~290 FLOP/B, so the HBM '
+                             'fraction (north star) is small by construction'},
         'kernels_ms': {'edge_stage': edge_ms, 'node_stage': node_ms,
                        'edge_share': timer.total_ms('edge_stage') / ms_total,
                        'node_share': timer.total_ms('node_stage') / ms_total},

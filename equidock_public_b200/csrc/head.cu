@@ -11,8 +11,8 @@
 namespace eqd {
 
 #define HEAD_THREADS 256
-#define HEAD_ULD 65   // padded row stride (doubles) of u[50][64]
-#define HEAD_HLD 65   // padded row stride (floats) of the staged h chunk
+#define HEAD_ULD 66   // padded row stride (doubles) of u[50][64]; even: rows are read as double2
+#define HEAD_HLD 66   // padded row stride (doubles) of the staged h chunk
 #define HEAD_JC 64    // nodes per staged chunk
 
 // ---- partial column sums of LeakyReLU(W_m h + b_m) over each node tile (:525, :529) -------------
@@ -66,7 +66,7 @@ __device__ __forceinline__ double warp_max_d(double v) {
   return v;
 }
 
-// ---- batched head algebra: the 1.6 MB of read-out weights are streamed ONCE per batch, not once per protein ---
+// ---- batched head algebra ---------------------------------------------------------------------------------------
 // qbar[s][64] = mean over segment s of LeakyReLU(W_m h + b_m)   (from the per-tile partial sums)
 __global__ void head_qbar_kernel(eqd_graph g, const float* __restrict__ part, const int* __restrict__ tile_ptr,
                                  double* __restrict__ qbar) {
@@ -76,130 +76,171 @@ __global__ void head_qbar_kernel(eqd_graph g, const float* __restrict__ part, co
   int n = g.seg_ptr[s + 1] - g.seg_ptr[s];
   qbar[(long)s * 64 + c] = n > 0 ? acc / (double)n : 0.0;
 }
-// qk[s][row] = <W_query[row], qbar[s]>, row < 3200.  CTA = 32 rows of W_query (smem) x all segments.
-__global__ void __launch_bounds__(256) head_qk_kernel(int nseg, eqd_head_params hp, const double* __restrict__ qbar,
-                                                      double* __restrict__ qk) {
-  __shared__ float w[32][65];
-  const int row0 = blockIdx.x * 32, tid = threadIdx.x;
-  for (int i = tid; i < 32 * 64; i += 256) w[i >> 6][i & 63] = hp.w_query[(long)(row0 + (i >> 6)) * 64 + (i & 63)];
-  __syncthreads();
-  const int rl = tid & 31, sl = tid >> 5;   // 32 rows x 8 segments per pass
-  for (int s = sl; s < nseg; s += 8) {
-    const double* qv = qbar + (long)s * 64;
-    double a0 = 0.0, a1 = 0.0;
-#pragma unroll 8
-    for (int d = 0; d < 64; d += 2) {
-      a0 = fma((double)w[rl][d], qv[d], a0);
-      a1 = fma((double)w[rl][d + 1], qv[d + 1], a1);
-    }
-    qk[(long)s * (EQD_HEADS * 64) + row0 + rl] = a0 + a1;
+
+// Weights-only fold, once per model:  m_qk[k][d'][d] = sum_e W_query[k*64+e][d'] W_key[k*64+e][d] / sqrt(64)
+// so that u_k = m_qk[k]^T qbar -- the 3200-d query never has to be formed per protein.  CTA = one head.
+__global__ void __launch_bounds__(256) head_fold_kernel(eqd_head_params hp, double* __restrict__ m_qk) {
+  __shared__ float wq[64][65], wk[64][65];
+  const int k = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < 64 * 64; i += 256) {
+    wq[i >> 6][i & 63] = hp.w_query[(long)k * 4096 + i];
+    wk[i >> 6][i & 63] = hp.w_key[(long)k * 4096 + i];
   }
-}
-// u[s][k][d] = sum_d' W_key[k*64+d'][d] * qk[partner(s)][k*64+d'] / sqrt(64).  CTA = one head k (W_key block in smem).
-__global__ void __launch_bounds__(256) head_u_kernel(int n_pairs, eqd_head_params hp, const double* __restrict__ qk,
-                                                     double* __restrict__ u) {
-  __shared__ float w[64][64];
-  const int k = blockIdx.x, tid = threadIdx.x, nseg = 2 * n_pairs;
-  for (int i = tid; i < 64 * 64; i += 256) w[i >> 6][i & 63] = hp.w_key[(long)k * 4096 + i];
   __syncthreads();
   const int d = tid & 63;
-  for (int s = blockIdx.y * 4 + (tid >> 6); s < nseg; s += gridDim.y * 4) {
-    const int ps = s < n_pairs ? s + n_pairs : s - n_pairs;   // the query comes from the partner protein (:544, :555)
-    const double* q = qk + (long)ps * (EQD_HEADS * 64) + k * 64;
-    double a0 = 0.0, a1 = 0.0;
-#pragma unroll 8
-    for (int dd = 0; dd < 64; dd += 2) {
-      a0 = fma((double)w[dd][d], q[dd], a0);
-      a1 = fma((double)w[dd + 1][d], q[dd + 1], a1);
-    }
-    u[((long)s * EQD_HEADS + k) * 64 + d] = (a0 + a1) * 0.125;  // / math.sqrt(d), d = 64 (:545)
+  for (int dq = tid >> 6; dq < 64; dq += 4) {
+    double a = 0.0;
+    for (int e = 0; e < 64; ++e) a = fma((double)wq[e][dq], (double)wk[e][d], a);
+    m_qk[((long)k * 64 + dq) * 64 + d] = a * 0.125;  // / math.sqrt(d), d = 64 (:545)
   }
 }
 
+// u[s][k][d] = sum_d' m_qk[k][d'][d] * qbar[partner(s)][d'].  CTA = one head k (its 32 KB fold in smem) x a stripe of
+// segments; a thread owns channels (lane, lane + 32) of 8 segments at a time (the qbar loads are warp-uniform
+// broadcasts): 4 shared + 8 global 16-byte loads feed 32 DFMAs.
+__global__ void __launch_bounds__(256) head_u_kernel(int n_pairs, const double* __restrict__ m_qk,
+                                                     const double* __restrict__ qbar, double* __restrict__ u) {
+  __shared__ double m[64][64];
+  const int k = blockIdx.x, tid = threadIdx.x, nseg = 2 * n_pairs;
+  for (int i = tid; i < 64 * 64; i += 256) m[i >> 6][i & 63] = m_qk[(long)k * 4096 + i];
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int s0 = blockIdx.y * 64 + warp * 8; s0 < nseg; s0 += gridDim.y * 64) {
+    const double* q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int s = min(s0 + j, nseg - 1);
+      int ps = s < n_pairs ? s + n_pairs : s - n_pairs;   // the query comes from the partner protein (:544, :555)
+      q[j] = qbar + (long)ps * 64;
+    }
+    double acc[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+#pragma unroll 2
+    for (int dd = 0; dd < 64; dd += 2) {
+      const double a0 = m[dd][lane], a1 = m[dd + 1][lane], b0 = m[dd][lane + 32], b1 = m[dd + 1][lane + 32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double2 qv = *reinterpret_cast<const double2*>(q[j] + dd);
+        acc[j][0] = fma(a1, qv.y, fma(a0, qv.x, acc[j][0]));
+        acc[j][1] = fma(b1, qv.y, fma(b0, qv.x, acc[j][1]));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (s0 + j < nseg) {
+        u[((long)(s0 + j) * EQD_HEADS + k) * 64 + lane] = acc[j][0];
+        u[((long)(s0 + j) * EQD_HEADS + k) * 64 + lane + 32] = acc[j][1];
+      }
+  }
+}
+
+// ---- keypoints: grid (segment, head half); 5 warps x 5 heads per CTA ------------------------------------------------
+#define KP_HEADS_PER_CTA 25
+#define KP_NH 5            // heads per warp
+#define KP_THREADS 160
 struct KeypSmem {
-  double u[EQD_HEADS * HEAD_ULD];
-  double state[EQD_HEADS * 5];  // running (max, sum, y.x, y.y, y.z) per head
-  float hc[HEAD_JC * HEAD_HLD];
+  double u[KP_HEADS_PER_CTA * HEAD_ULD];
+  double hc[HEAD_JC * HEAD_HLD];  // the staged h chunk, already widened to fp64
   double xc[HEAD_JC * 3];
 };
 
-// One CTA per segment s (a protein): keypoints Y_s[50][3] (:542-560).
-__global__ void __launch_bounds__(HEAD_THREADS)
+// One CTA per (protein s, 25 of the 50 heads): keypoints Y_s[k][3] (:542-560).  Warp w owns heads 25 y + 5 w + j; every
+// lane keeps its OWN online-softmax state (max, sum, sum p x) per head over the rows it sees (rows lane, lane + 32 of each
+// 64-row chunk), so the chunk loop has no cross-lane traffic at all; the 32 partial states are merged once at the end.
+__global__ void __launch_bounds__(KP_THREADS, 4)
 keypoints_kernel(eqd_graph g, const float* __restrict__ h, const double* __restrict__ x,
                  const double* __restrict__ u_all /* [2B][50][64] */, double* __restrict__ keypts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KeypSmem& s = *reinterpret_cast<KeypSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int seg = blockIdx.x;
+  const int seg = blockIdx.x, head0 = blockIdx.y * KP_HEADS_PER_CTA;
   const int i0 = g.seg_ptr[seg], i1 = g.seg_ptr[seg + 1];
 
-  for (int o = tid; o < EQD_HEADS * 64; o += HEAD_THREADS) s.u[(o >> 6) * HEAD_ULD + (o & 63)] = u_all[(long)seg * (EQD_HEADS * 64) + o];
-  if (tid < EQD_HEADS) {
-    s.state[tid * 5 + 0] = -INFINITY;
-    s.state[tid * 5 + 1] = 0.0;
-    s.state[tid * 5 + 2] = 0.0;
-    s.state[tid * 5 + 3] = 0.0;
-    s.state[tid * 5 + 4] = 0.0;
-  }
-  __syncthreads();
+  for (int o = tid; o < KP_HEADS_PER_CTA * 64; o += KP_THREADS)
+    s.u[(o >> 6) * HEAD_ULD + (o & 63)] = u_all[((long)seg * EQD_HEADS + head0) * 64 + o];
 
-  // online softmax over this protein's nodes, chunk by chunk; warp w owns heads w, w+8, ...
+  double m[KP_NH], l[KP_NH], sx[KP_NH], sy[KP_NH], sz[KP_NH];
+#pragma unroll
+  for (int j = 0; j < KP_NH; ++j) {
+    m[j] = -INFINITY;
+    l[j] = sx[j] = sy[j] = sz[j] = 0.0;
+  }
+  const double* uw = s.u + (warp * KP_NH) * HEAD_ULD;
+  const double* h0r = s.hc + lane * HEAD_HLD;
+  const double* h1r = s.hc + (lane + 32) * HEAD_HLD;
+
   for (int c0 = i0; c0 < i1; c0 += HEAD_JC) {
     const int nc = min(HEAD_JC, i1 - c0);
-    for (int idx = tid; idx < HEAD_JC * 64; idx += HEAD_THREADS) {
-      int r = idx >> 6, d = idx & 63;
-      s.hc[r * HEAD_HLD + d] = r < nc ? h[(long)(c0 + r) * EQD_HID + d] : 0.f;
+    __syncthreads();   // the previous chunk (and, first time round, u) is no longer / now visible
+    for (int idx = tid; idx < HEAD_JC * 16; idx += KP_THREADS) {
+      const int r = idx >> 4, d4 = (idx & 15) * 4;
+      float4 v = r < nc ? *reinterpret_cast<const float4*>(h + (long)(c0 + r) * EQD_HID + d4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      double* dst = s.hc + r * HEAD_HLD + d4;
+      *reinterpret_cast<double2*>(dst) = make_double2((double)v.x, (double)v.y);
+      *reinterpret_cast<double2*>(dst + 2) = make_double2((double)v.z, (double)v.w);
     }
-    for (int idx = tid; idx < HEAD_JC * 3; idx += HEAD_THREADS) s.xc[idx] = idx < nc * 3 ? x[(long)c0 * 3 + idx] : 0.0;
+    for (int idx = tid; idx < HEAD_JC * 3; idx += KP_THREADS) s.xc[idx] = idx < nc * 3 ? x[(long)c0 * 3 + idx] : 0.0;
     __syncthreads();
-    for (int k = warp; k < EQD_HEADS; k += HEAD_THREADS / 32) {
-      const double* uk = s.u + k * HEAD_ULD;
-      double lg[2];
+    // logits of this warp's 5 heads for 2 rows: 7 16-byte shared loads feed 20 DFMAs per pair of channels
+    double lg[KP_NH][2];
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        int r = lane + 32 * q;
-        const float* hr = s.hc + r * HEAD_HLD;
-        double v = 0.0;
-#pragma unroll 8
-        for (int d = 0; d < 64; ++d) v = fma((double)hr[d], uk[d], v);
-        lg[q] = r < nc ? v : -INFINITY;
-      }
-      double cmax = warp_max_d(fmax(lg[0], lg[1]));
-      double mold = s.state[k * 5 + 0];
-      double mnew = fmax(mold, cmax);
-      double ps = 0.0, px = 0.0, py = 0.0, pz = 0.0;
+    for (int j = 0; j < KP_NH; ++j) lg[j][0] = lg[j][1] = 0.0;
+    if (nc > 32) {
+#pragma unroll 4
+      for (int d = 0; d < 64; d += 2) {
+        const double2 a = *reinterpret_cast<const double2*>(h0r + d), b = *reinterpret_cast<const double2*>(h1r + d);
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        int r = lane + 32 * q;
-        double pj = r < nc ? exp(lg[q] - mnew) : 0.0;
-        ps += pj;
-        px += pj * s.xc[r * 3 + 0];
-        py += pj * s.xc[r * 3 + 1];
-        pz += pj * s.xc[r * 3 + 2];
+        for (int j = 0; j < KP_NH; ++j) {
+          const double2 uv = *reinterpret_cast<const double2*>(uw + j * HEAD_ULD + d);
+          lg[j][0] = fma(a.y, uv.y, fma(a.x, uv.x, lg[j][0]));
+          lg[j][1] = fma(b.y, uv.y, fma(b.x, uv.x, lg[j][1]));
+        }
       }
-      ps = warp_sum_d(ps);
-      px = warp_sum_d(px);
-      py = warp_sum_d(py);
-      pz = warp_sum_d(pz);
-      __syncwarp();
-      if (lane == 0) {
-        double scale = exp(mold - mnew);  // exp(-inf) = 0 on the first chunk
-        s.state[k * 5 + 0] = mnew;
-        s.state[k * 5 + 1] = s.state[k * 5 + 1] * scale + ps;
-        s.state[k * 5 + 2] = s.state[k * 5 + 2] * scale + px;
-        s.state[k * 5 + 3] = s.state[k * 5 + 3] * scale + py;
-        s.state[k * 5 + 4] = s.state[k * 5 + 4] * scale + pz;
+    } else {   // a short last chunk: only the first row of each lane exists
+#pragma unroll 4
+      for (int d = 0; d < 64; d += 2) {
+        const double2 a = *reinterpret_cast<const double2*>(h0r + d);
+#pragma unroll
+        for (int j = 0; j < KP_NH; ++j) {
+          const double2 uv = *reinterpret_cast<const double2*>(uw + j * HEAD_ULD + d);
+          lg[j][0] = fma(a.y, uv.y, fma(a.x, uv.x, lg[j][0]));
+        }
       }
-      __syncwarp();
     }
-    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int r = lane + 32 * q;
+      if (r < nc) {
+        const double px = s.xc[r * 3 + 0], py = s.xc[r * 3 + 1], pz = s.xc[r * 3 + 2];
+#pragma unroll
+        for (int j = 0; j < KP_NH; ++j) {
+          const double dlt = lg[j][q] - m[j];       // +inf on the lane's first row
+          const double e = exp(-fabs(dlt));
+          const bool up = dlt > 0.0;
+          const double pj = up ? 1.0 : e, sc = up ? e : 1.0;
+          m[j] = up ? lg[j][q] : m[j];
+          l[j] = fma(l[j], sc, pj);
+          sx[j] = fma(sx[j], sc, pj * px);
+          sy[j] = fma(sy[j], sc, pj * py);
+          sz[j] = fma(sz[j], sc, pj * pz);
+        }
+      }
+    }
   }
-  if (tid < EQD_HEADS) {
-    double inv = 1.0 / s.state[tid * 5 + 1];
-    double* y = keypts + ((long)seg * EQD_HEADS + tid) * 3;
-    y[0] = s.state[tid * 5 + 2] * inv;
-    y[1] = s.state[tid * 5 + 3] * inv;
-    y[2] = s.state[tid * 5 + 4] * inv;
+  // merge the 32 per-lane states of each head
+#pragma unroll
+  for (int j = 0; j < KP_NH; ++j) {
+    const double mm = warp_max_d(m[j]);
+    const double sc = m[j] == -INFINITY ? 0.0 : exp(m[j] - mm);
+    const double lt = warp_sum_d(l[j] * sc), ax = warp_sum_d(sx[j] * sc), ay = warp_sum_d(sy[j] * sc), az = warp_sum_d(sz[j] * sc);
+    if (lane == 0) {
+      const double inv = 1.0 / lt;
+      double* y = keypts + ((long)seg * EQD_HEADS + head0 + warp * KP_NH + j) * 3;
+      y[0] = ax * inv;
+      y[1] = ay * inv;
+      y[2] = az * inv;
+    }
   }
 }
 
@@ -399,18 +440,26 @@ extern "C" int eqd_abi_version(void) { return EQD_ABI_VERSION; }
 static inline size_t ws_part_bytes(int32_t n_node_tiles) { return eqd_align256((size_t)(n_node_tiles > 0 ? n_node_tiles : 1) * 64 * sizeof(float)); }
 static inline size_t ws_tile_ptr_bytes(int32_t n_pairs) { return eqd_align256((size_t)(2 * (n_pairs > 0 ? n_pairs : 0) + 1) * sizeof(int)); }
 static inline size_t ws_qbar_bytes(int32_t n_pairs) { return eqd_align256((size_t)2 * (n_pairs > 0 ? n_pairs : 1) * 64 * sizeof(double)); }
-static inline size_t ws_qk_bytes(int32_t n_pairs) { return eqd_align256((size_t)2 * (n_pairs > 0 ? n_pairs : 1) * EQD_HEADS * 64 * sizeof(double)); }
+static inline size_t ws_u_bytes(int32_t n_pairs) { return eqd_align256((size_t)2 * (n_pairs > 0 ? n_pairs : 1) * EQD_HEADS * 64 * sizeof(double)); }
 
 extern "C" size_t eqd_workspace_bytes(int32_t n_nodes, int32_t n_node_tiles, int32_t n_pairs) {
   (void)n_nodes;
-  // per-tile partial sums | first tile of each segment | qbar[2B][64] | qk[2B][3200] | u[2B][50][64]   (fp64 from qbar on)
-  return ws_part_bytes(n_node_tiles) + ws_tile_ptr_bytes(n_pairs) + ws_qbar_bytes(n_pairs) + 2 * ws_qk_bytes(n_pairs);
+  // per-tile partial sums | first tile of each segment | qbar[2B][64] | u[2B][50][64]   (fp64 from qbar on)
+  return ws_part_bytes(n_node_tiles) + ws_tile_ptr_bytes(n_pairs) + ws_qbar_bytes(n_pairs) + ws_u_bytes(n_pairs);
+}
+
+extern "C" int eqd_head_fold(const eqd_head_params* hp, double* m_qk, void* stream) {
+  if (!hp || !hp->w_key || !hp->w_query || !m_qk) return EQD_ERR_BAD_ARG;
+  eqd::head_fold_kernel<<<EQD_HEADS, 256, 0, (cudaStream_t)stream>>>(*hp, m_qk);
+  EQD_CUDA_LAUNCH_CHECK();
+  return EQD_OK;
 }
 
 extern "C" int eqd_keypoints(const eqd_graph* g, const eqd_head_params* hp, const float* h, const double* x,
                              void* workspace, size_t workspace_bytes, double* keypts, double* ymean, double* cov,
                              void* stream) {
   if (!g || !hp || !h || !x || !workspace || !keypts || !ymean || !cov) return EQD_ERR_BAD_ARG;
+  if (!hp->m_qk || (reinterpret_cast<uintptr_t>(hp->m_qk) & 15)) return EQD_ERR_BAD_ARG;   // eqd_head_fold() output
   if (workspace_bytes < eqd_workspace_bytes(g->n_nodes, g->n_node_tiles, g->n_pairs)) return EQD_ERR_WORKSPACE;
   if (!(hp->leaky_slope >= 0.f && hp->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;
   if (g->n_pairs <= 0) return EQD_OK;
@@ -419,8 +468,7 @@ extern "C" int eqd_keypoints(const eqd_graph* g, const eqd_head_params* hp, cons
   float* part = reinterpret_cast<float*>(wsb);
   int* tile_ptr = reinterpret_cast<int*>(wsb + ws_part_bytes(g->n_node_tiles));
   double* qbar = reinterpret_cast<double*>(wsb + ws_part_bytes(g->n_node_tiles) + ws_tile_ptr_bytes(g->n_pairs));
-  double* qk = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(qbar) + ws_qbar_bytes(g->n_pairs));
-  double* u = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(qk) + ws_qk_bytes(g->n_pairs));
+  double* u = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(qbar) + ws_qbar_bytes(g->n_pairs));
   const int nseg = 2 * g->n_pairs;
   {
     size_t smem = (size_t)(EQD_TM * 68 + 2 * EQD_WCHUNK * EQD_WLD) * sizeof(float);
@@ -434,17 +482,15 @@ extern "C" int eqd_keypoints(const eqd_graph* g, const eqd_head_params* hp, cons
     EQD_CUDA_LAUNCH_CHECK();
     eqd::head_qbar_kernel<<<nseg, 64, 0, st>>>(*g, part, tile_ptr, qbar);
     EQD_CUDA_LAUNCH_CHECK();
-    eqd::head_qk_kernel<<<EQD_HEADS * 64 / 32, 256, 0, st>>>(nseg, *hp, qbar, qk);
-    EQD_CUDA_LAUNCH_CHECK();
-    int gy = (nseg + 3) / 4;
+    int gy = (nseg + 63) / 64;
     if (gy > 8) gy = 8;
-    eqd::head_u_kernel<<<dim3(EQD_HEADS, gy), 256, 0, st>>>(g->n_pairs, *hp, qk, u);
+    eqd::head_u_kernel<<<dim3(EQD_HEADS, gy), 256, 0, st>>>(g->n_pairs, hp->m_qk, qbar, u);
     EQD_CUDA_LAUNCH_CHECK();
   }
   {
     size_t smem = sizeof(eqd::KeypSmem);
     cudaFuncSetAttribute(eqd::keypoints_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    eqd::keypoints_kernel<<<2 * g->n_pairs, HEAD_THREADS, smem, st>>>(*g, h, x, u, keypts);
+    eqd::keypoints_kernel<<<dim3(2 * g->n_pairs, EQD_HEADS / KP_HEADS_PER_CTA), KP_THREADS, smem, st>>>(*g, h, x, u, keypts);
     EQD_CUDA_LAUNCH_CHECK();
   }
   {

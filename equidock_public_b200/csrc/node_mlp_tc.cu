@@ -14,8 +14,11 @@ namespace eqd {
 
 struct NmConsts { float b5[64], ln_g[64], ln_b[64], b6[64]; };
 
+#define NM_SC_LD 36   // padded row stride (floats) of a warp's 32 x 32 transposition scratch: conflict-free both ways
+
 struct NmSmem {
   unsigned char w[NM_W_BYTES];
+  float sc[NM_THREADS / 32][32 * NM_SC_LD];   // one 32-row x 128-byte scratch per warp (its rows x its column half)
   float red[2][EQD_TM * 4];
   unsigned long long w_bar, a_bar[2][2];
   unsigned int tmem_base;
@@ -73,18 +76,35 @@ node_mlp_tc_kernel(int n_nodes, eqd_layer_params p, const __grid_constant__ NmCo
     tc_fence_after();
   };
 
+  // Global rows travel coalesced: the warp's 32 rows x 128 bytes (its column half) are cp.async'ed into its scratch,
+  // 8 lanes per row, one piece ahead of its use; each thread then picks up its own row.
+  const int lane = tid & 31, wrow0 = 32 * (warp & 3);
+  float* sc = S.sc[warp];
+  auto fetch = [&](const float* base, int ld, int t) {
+    if (t >= ntiles) return;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = i * 4 + (lane >> 3);
+      const long nd = (long)t * EQD_TM + wrow0 + row;
+      const bool ok = nd < n_nodes;   // src-size 0 zero-fills
+      cp_async16(sc + row * NM_SC_LD + (lane & 7) * 4, base + (ok ? nd : 0) * ld + half * 32 + (lane & 7) * 4, ok);
+    }
+    cp_async_commit();
+  };
+  auto take = [&](float (&v)[32]) {
+    cp_async_wait<0>();
+    __syncwarp();
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      float4 t = *reinterpret_cast<const float4*>(sc + lane * NM_SC_LD + c4 * 4);
+      v[c4 * 4] = t.x; v[c4 * 4 + 1] = t.y; v[c4 * 4 + 2] = t.z; v[c4 * 4 + 3] = t.w;
+    }
+    __syncwarp();
+  };
+  fetch(h_in, EQD_HID, blockIdx.x * 2 + wg);
   for (int tile = blockIdx.x * 2 + wg; tile < ntiles; tile += gridDim.x * 2) {
     const int node = tile * EQD_TM + r;
     const bool valid = node < n_nodes;
-    float hskip[32];
-    auto load32 = [&](const float* base, int ld, int col0, float (&v)[32]) {
-      const float4* sp = reinterpret_cast<const float4*>(base + (long)node * ld + col0 + half * 32);
-#pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        float4 t = valid ? sp[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[c4 * 4] = t.x; v[c4 * 4 + 1] = t.y; v[c4 * 4 + 2] = t.z; v[c4 * 4 + 3] = t.w;
-      }
-    };
     // ---- node_mlp.0 over [h | aggr | mu | h0] in 5 K-pieces ---------------------------------------------------
     // The tensor core truncates (round-toward-zero) on every add into an fp32 accumulator: a bias that grows with
     // the number of accumulation steps.  Each 64-wide piece is therefore its own accumulation (4 full-magnitude
@@ -92,8 +112,12 @@ node_mlp_tc_kernel(int n_nodes, eqd_layer_params p, const __grid_constant__ NmCo
     float acc[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) acc[c] = cst.b5[half * 32 + c];
-    load32(h_in, EQD_HID, 0, hskip);
-    store_half_split3(tmem + 64 + half * 16, hskip);       // piece 0 (h) -> A
+    {
+      float v[32];
+      take(v);
+      fetch(aggr, EQD_HID, tile);
+      store_half_split3(tmem + 64 + half * 16, v);         // piece 0 (h) -> A
+    }
     tc_fence_before();
     wg_barrier(wg);
     issue(0, 0, NM_W5_SPLIT, 4, 0);
@@ -105,19 +129,21 @@ node_mlp_tc_kernel(int n_nodes, eqd_layer_params p, const __grid_constant__ NmCo
 #pragma unroll
         for (int c = 0; c < 32; ++c) acc[c] += d[c];
       };
-      load32(aggr, EQD_HID, 0, v);
+      take(v);
+      fetch(mu, EQD_HID, tile);
       drain();
       store_half_split3(tmem + 64 + half * 16, v);         // piece 1 (aggr)
       tc_fence_before();
       wg_barrier(wg);
       issue(0, 4 * 2048, NM_W5_SPLIT, 4, 0);
-      load32(mu, EQD_HID, 0, v);
+      take(v);
+      fetch(h0, EQD_H0_PAD, tile);
       drain();
       store_half_split3(tmem + 64 + half * 16, v);         // piece 2 (mu)
       tc_fence_before();
       wg_barrier(wg);
       issue(0, 8 * 2048, NM_W5_SPLIT, 4, 0);
-      load32(h0, EQD_H0_PAD, 0, v);
+      take(v);
       drain();
       store_half_split3(tmem + 64 + half * 16, v);         // piece 3 (h0[0:64])
       tc_fence_before();
@@ -177,19 +203,30 @@ node_mlp_tc_kernel(int n_nodes, eqd_layer_params p, const __grid_constant__ NmCo
     tc_fence_before();
     wg_barrier(wg);
     issue(0, NM_W6_BASE, NM_W6_SPLIT, 4, 0);
+    fetch(h_in, EQD_HID, tile);   // the skip operand again (an L2 hit) rather than 32 registers held across the tile
     wait_a(0);
     {
-      float v[32];
+      float v[32], hskip[32];
+      take(hskip);
       tmem_ld32f(tmem + half * 32, v);
       const float sk = p.skip_weight_h, sk1 = 1.f - p.skip_weight_h;
 #pragma unroll
       for (int c = 0; c < 32; ++c) v[c] = sk * (v[c] + cst.b6[half * 32 + c]) + sk1 * hskip[c];  // :332-334
-      if (valid) {
-        float4* o = reinterpret_cast<float4*>(h_out + (long)node * EQD_HID + half * 32);
+      // transposed through the scratch: 8 lanes write one contiguous 128-byte half row
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) o[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+      for (int c4 = 0; c4 < 8; ++c4)
+        *reinterpret_cast<float4*>(sc + lane * NM_SC_LD + c4 * 4) = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+      __syncwarp();
+      float* o = h_out + ((long)tile * EQD_TM + wrow0) * EQD_HID + half * 32 + (lane & 7) * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + (lane >> 3);
+        float4 t = *reinterpret_cast<const float4*>(sc + row * NM_SC_LD + (lane & 7) * 4);
+        if ((long)tile * EQD_TM + wrow0 + row < n_nodes) *reinterpret_cast<float4*>(o + (long)row * EQD_HID) = t;
       }
+      __syncwarp();
     }
+    fetch(h_in, EQD_HID, tile + gridDim.x * 2);   // next tile's h rows, behind the end-of-tile barrier
     tc_fence_before();
     wg_barrier(wg);  // D and both A buffers are free for the next tile
   }

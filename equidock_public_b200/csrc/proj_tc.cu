@@ -14,8 +14,11 @@ namespace eqd {
 
 struct PjConsts { float b[320]; };
 
+#define PJ_SC_LD 36   // padded row stride (floats) of a warp's 32 x 32 transposition scratch: conflict-free both ways
+
 struct PjSmem {
   unsigned char w[PJ_W_BYTES];
+  float sc[PJ_THREADS / 32][32 * PJ_SC_LD];   // one 32-row x 128-byte scratch per warp (its rows x its column half)
   unsigned long long w_bar, d_bar[2][2];
   unsigned int tmem_base;
 };
@@ -79,18 +82,37 @@ project_tc_kernel(int n_nodes, eqd_layer_params p, const __grid_constant__ PjCon
     }
   };
 
+  const int lane = tid & 31, wrow0 = 32 * (warp & 3);
+  float* sc = S.sc[warp];
+  // coalesced cp.async of this warp's 32 rows x [half*32, +32) of tile t into its scratch (zeros past the end)
+  auto load_rows = [&](int t) {
+    if (t >= ntiles) return;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = i * 4 + (lane >> 3);
+      const long nd = (long)t * EQD_TM + wrow0 + row;
+      float* dst = sc + row * PJ_SC_LD + (lane & 7) * 4;
+      const bool ok = nd < n_nodes;   // src-size 0 zero-fills
+      cp_async16(dst, h + (ok ? nd : 0) * EQD_HID + half * 32 + (lane & 7) * 4, ok);
+    }
+    cp_async_commit();
+  };
+  load_rows(blockIdx.x * 2 + wg);
   for (int tile = blockIdx.x * 2 + wg; tile < ntiles; tile += gridDim.x * 2) {
     const int node0 = tile * EQD_TM;
     const int node = node0 + r;
     const bool valid = node < n_nodes;
     {
+      // the warp's 32 rows x 128 bytes arrive coalesced (8 lanes per row) in its scratch; each thread then reads its row
+      cp_async_wait<0>();
+      __syncwarp();
       float v[32];
-      const float4* hp = reinterpret_cast<const float4*>(h + (long)node * EQD_HID + half * 32);
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) {
-        float4 t = valid ? hp[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 t = *reinterpret_cast<const float4*>(sc + lane * PJ_SC_LD + c4 * 4);
         v[c4 * 4] = t.x; v[c4 * 4 + 1] = t.y; v[c4 * 4 + 2] = t.z; v[c4 * 4 + 3] = t.w;
       }
+      __syncwarp();
       store_half_split3(a_col + half * 16, v);
     }
     tc_fence_before();
@@ -114,13 +136,26 @@ project_tc_kernel(int n_nodes, eqd_layer_params p, const __grid_constant__ PjCon
         float t = v[c] + cst.b[grp * 64 + half * 32 + c];
         v[c] = act ? lrelu(t, slope) : t;
       }
-      if (valid) {
-        float4* o = reinterpret_cast<float4*>(proj + (long)node * 320 + grp * 64 + half * 32);
+      if (grp < 3 || kv == nullptr) {   // with K/V blocks requested nobody reads the fp32 K / V columns: skip 2 x 256 B / node
+        // transpose through the warp's scratch so that 8 lanes write one contiguous 128-byte half row (full sectors)
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) o[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
-        if (grp >= 3 && kv != nullptr) store_kv_blocks(kv + (long)(grp - 3) * 3 * kv_split_stride, kv_split_stride, node, half, v);
+        for (int c4 = 0; c4 < 8; ++c4)
+          *reinterpret_cast<float4*>(sc + lane * PJ_SC_LD + c4 * 4) = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+        __syncwarp();
+        float* o = proj + (long)(node0 + wrow0) * 320 + grp * 64 + half * 32 + (lane & 7) * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + (lane >> 3);
+          float4 t = *reinterpret_cast<const float4*>(sc + row * PJ_SC_LD + (lane & 7) * 4);
+          if (node0 + wrow0 + row < n_nodes) *reinterpret_cast<float4*>(o + (long)row * 320) = t;
+        }
+        __syncwarp();
       }
+      if (valid && grp >= 3 && kv != nullptr)
+        store_kv_blocks(kv + (long)(grp - 3) * 3 * kv_split_stride, kv_split_stride, node, half, v);
     }
+    // next tile's rows -> scratch (lands behind the end-of-tile barrier and the other group's work)
+    load_rows(tile + gridDim.x * 2);
     tc_fence_before();
     wg_barrier(wg);  // A may be overwritten by the next tile
   }

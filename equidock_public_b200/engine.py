@@ -128,6 +128,12 @@ class PackedHead:
             setattr(s, k, v.data_ptr())
         s.leaky_slope = leaky_slope
         self.struct = s
+        # weights-only fold of the 50-head key / query projections (eqd_head_fold), done once per model on the device
+        self.m_qk = torch.empty(nat.HEADS, nat.HID, nat.HID, dtype=torch.float64, device=device)
+        with torch.cuda.device(device):
+            nat.check(nat.load().eqd_head_fold(C.byref(s), self.m_qk.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                      'eqd_head_fold')
+        s.m_qk = self.m_qk.data_ptr()
 
 
 class GraphPlan:
@@ -228,8 +234,8 @@ class IEGMNEngine:
     def launches_per_forward(n_layers: int) -> int:
         """Kernels of csrc/ launched by one forward: embed, project (layer 0), per layer edge stage + node stage
         (layer 0: fp32 node kernel + K/V blocks; 64-wide layers: attention, node MLP, next projections),
-        then head_mean, tile_ptr, head_qbar, head_qk, head_u, keypoints, keypoint_cov, kabsch_apply."""
-        n = 2 + 8
+        then head_mean, tile_ptr, head_qbar, head_u, keypoints, keypoint_cov, kabsch_apply."""
+        n = 2 + 7
         for li in range(n_layers):
             last = li == n_layers - 1
             n += 1 + ((1 + (0 if last else 1)) if li == 0 else (2 + (0 if last else 1)))

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define EQD_ABI_VERSION 3
+#define EQD_ABI_VERSION 4
 
 #define EQD_EDGE_FEATS 27     /* input_edge_feats_dim, protein_utils.py:71-86 + :373-389 */
 #define EQD_N_RBF 15          /* all_sigmas_dist = 1.5**s, rigid_docking_model.py:116 */
@@ -135,6 +135,8 @@ typedef struct eqd_head_params {
   const float* b_mean;        /* [64] */
   const float* w_key;         /* [3200][64] att_mlp_key_ROT.0.weight, as in the state_dict */
   const float* w_query;       /* [3200][64] att_mlp_query_ROT.0.weight, as in the state_dict */
+  const double* m_qk;         /* [50][64][64] fp64, written once per model by eqd_head_fold() from w_key / w_query:
+                                 m_qk[k][d'][d] = sum_e w_query[64k+e][d'] w_key[64k+e][d] / 8.  Device memory, 16-byte aligned. */
   float leaky_slope;
 } eqd_head_params;
 
@@ -181,7 +183,8 @@ int eqd_node_stage(const eqd_graph* g, const eqd_layer_params* p, const eqd_laye
  * K and V of every node travel as bf16x3 "8-node blocks": kv[which 2 (K,V)][split 3][n/8 (+8 zero pad
  * blocks)][d/8][n%8][d%8] bf16 (1 KB per block), so a run of blocks is a ready UMMA B operand for TMA.   */
 size_t eqd_kv_blocks_bytes(int32_t n_nodes);
-/* proj[n][320] = [Psrc|Pdst|Q|K|V](h[n]) for a dh==64 layer, plus its K/V blocks (kv may be NULL). */
+/* proj[n][320] = [Psrc|Pdst|Q|K|V](h[n]) for a dh==64 layer.  With kv != NULL, K and V are written ONLY as
+ * bf16x3 blocks into kv and the fp32 columns 192..319 of proj are left untouched (nothing downstream reads them). */
 int eqd_project_tc(const eqd_graph* g, const eqd_layer_params* p, const float* h /*[n][64]*/, float* proj,
                    void* kv, void* stream);
 /* K/V blocks from the fp32 columns of an existing projection buffer (row stride pw floats). */
@@ -206,6 +209,11 @@ int eqd_iegmn_layer_forward(const eqd_graph* g, const eqd_layer_params* p, const
                             const double* x_in, const double* x_orig,
                             float* proj, float* proj_next, float* aggr,
                             float* h_out, double* x_out, int32_t* status, void* stream);
+
+/* Weights-only fold of the 50-head key / query projections (att_mlp_key_ROT, att_mlp_query_ROT :427-438) into
+ * m_qk (see eqd_head_params), so that the per-protein logits are h_j . (m_qk[k]^T qbar) (:544-546, :555-557).
+ * Call once after loading a checkpoint; eqd_keypoints() reads hp->m_qk.                                       */
+int eqd_head_fold(const eqd_head_params* hp, double* m_qk /*[50][64][64]*/, void* stream);
 
 /* Keypoint read-out (IEGMN.forward :521-567): mean-pooled queries, 50-head attention over each
  * protein's nodes, keypoints Y (fp64 [2B][50][3], segment order), their means and the 3x3

@@ -26,7 +26,8 @@ for desc, prs in (('golden dips x4', [pairs[n] for n in names]), ('synthetic 6x(
     kvb = lib.eqd_kv_blocks_bytes(N)
     kv = torch.zeros(kvb, dtype=torch.uint8, device=dev)
     assert lib.eqd_project(G, L, nat.ptr(h), 64, nat.ptr(proj_ff), None) == 0
-    assert lib.eqd_project_tc(G, L, nat.ptr(h), nat.ptr(proj_tc), nat.ptr(kv), None) == 0
+    assert lib.eqd_project_tc(G, L, nat.ptr(h), nat.ptr(proj_tc), None, None) == 0      # all 5 groups as fp32
+    assert lib.eqd_project_tc(G, L, nat.ptr(h), nat.ptr(proj_tc), nat.ptr(kv), None) == 0  # + K/V blocks
     torch.cuda.synchronize()
     w1 = sd[pre + 'edge_mlp.0.weight']; b1 = sd[pre + 'edge_mlp.0.bias']
     lr = lambda t: torch.nn.functional.leaky_relu(t, 0.01)

@@ -46,7 +46,8 @@ def test_struct_layouts_are_natural_c_layouts():
     assert nat.EqdLayerParams.w_edge_tc.offset == 96 and nat.EqdLayerParams.edge_consts_host.offset == 104
     assert nat.EqdLayerParams.w_node_tc.offset == 112 and nat.EqdLayerParams.proj_bias_host.offset == 136
     assert nat.EqdLayerParams.w_node1.offset == 144
-    assert ctypes.sizeof(nat.EqdHeadParams) == 4 * 8 + 8
+    assert ctypes.sizeof(nat.EqdHeadParams) == 5 * 8 + 8
+    assert nat.EqdHeadParams.m_qk.offset == 32 and nat.EqdHeadParams.leaky_slope.offset == 40
 
 
 def test_workspace_bytes_host_arithmetic():
@@ -163,4 +164,4 @@ def test_unsupported_configurations_raise():
 
 
 def test_launch_accounting():
-    assert IEGMNEngine.launches_per_forward(8) == 40 and IEGMNEngine.launches_per_forward(5) == 28
+    assert IEGMNEngine.launches_per_forward(8) == 39 and IEGMNEngine.launches_per_forward(5) == 27
