@@ -30,9 +30,9 @@ namespace eqd {
 
 struct TcWgSmem {                         // per warpgroup
   float stage[EQD_TM * TC_LD];            // gathered Psrc rows, later the fp32 msg tile
-  float pdst[TC_MAX_TN * TC_LD];          // Pdst rows of the tile's destination nodes
+  float pdst[2][TC_MAX_TN * TC_LD];       // Pdst rows of the tile's destination nodes (prefetched one tile ahead)
   float he[TC_HE_STAGE_FLOATS];           // raw he rows of the tile (bulk-copied, 16B-aligned chunks)
-  double xm[EQD_TM * 3];                  // x_rel * phi per edge
+  double xm[EQD_TM * 3];                  // x_rel per edge (scaled by phi in the coordinate update)
   double xs[EQD_TM * 6];                  // x[src], x[dst] of the tile's edges (prefetched one tile ahead)
   double red[EQD_TM * 4];                 // per-row partial reductions exchanged between the two column halves
   int src[2][EQD_TM];
@@ -43,7 +43,7 @@ struct TcWgSmem {                         // per warpgroup
 struct TcSmem {
   unsigned char w[TC_W_BYTES];            // bf16x3 weights, canonical K-major no-swizzle UMMA layout
   TcWgSmem wg[2];
-  unsigned long long w_bar, mma_bar[2], he_bar[2];
+  unsigned long long w_bar, mma_bar[2], mma2_bar[2], he_bar[2], a_bar[2];
   unsigned int tmem_base;
 };
 
@@ -77,6 +77,10 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     mbar_init(&S.mma_bar[1], 1);
     mbar_init(&S.he_bar[0], 1);
     mbar_init(&S.he_bar[1], 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&S.mma2_bar[a], 1);
+      mbar_init(&S.a_bar[a], 8);      // one arrival per warp of the tile group: "my part of the A operand is in TMEM"
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(&S.w_bar, TC_W_BYTES);
     bulk_g2s(S.w, p.w_edge_tc, TC_W_BYTES, &S.w_bar);
@@ -95,7 +99,7 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
   const unsigned d_col = tmem + half * 32;                                         // my half of D (64 columns)
   const unsigned a_col = tmem + 128;                                               // A: 3 splits x 32 columns (D: 0..127)
   mbar_wait(&S.w_bar, 0);
-  unsigned mma_phase = 0, he_phase = 0;
+  unsigned mma_phase = 0, mma2_phase = 0, he_phase = 0, a_phase = 0;
   const unsigned w_saddr = smem_u32(S.w);
 
   // Prefetch of a tile's indices + he rows (issued by the half-0 threads).
@@ -134,6 +138,10 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
         br = (unsigned)(((b1 + 15) & ~15L) - sr);
         off_r = (int)(dst_r_off >> 2) + (int)((b0 - sr) >> 2);
       }
+      for (int idx = q; idx < nn * 16; idx += 256) {   // Pdst rows of the tile's (contiguous) destination nodes
+        int row = idx >> 4, c4 = idx & 15;
+        cp_async16(&W.pdst[buf][row * TC_LD + c4 * 4], proj + (long)(n0 + row) * pw + 64 + c4 * 4, true);
+      }
       if (q == 0) {
         mbar_expect_tx(&S.he_bar[wg], bl + br);
         if (bl) bulk_g2s(W.he, reinterpret_cast<const unsigned char*>(g.he_lig) + sl, bl, &S.he_bar[wg]);
@@ -158,6 +166,8 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
   if (wg == 1 && stagger_ns > 0) __nanosleep(stagger_ns);
   int tile = blockIdx.x * 2 + wg;
   const int tstride = gridDim.x * 2;
+  const int lane = tid & 31, wrow0 = 32 * (warp & 3);
+  const int pair_id = 3 + wg * 4 + (warp & 3);   // named barrier of the two warps that hold rows [wrow0, wrow0 + 32)
   int buf = 0;
   int e0 = 0, ne = 0, off_l = 0, n_l = 0, off_r = 0;
   if (tile < ntiles) {
@@ -184,12 +194,15 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
       e0 = e0n; ne = nen; off_l = off_ln; n_l = n_ln; off_r = off_rn; buf ^= 1;
       continue;
     }
-    // ---- S0/S1: indices + coordinates ready; gathers; geometry; [he|rbf] -> TMEM -----------------------
+    // ---- S0/S1: indices + coordinates ready; geometry; [he|rbf] -> TMEM ---------------------------------------
+    // Synchronisation inside a tile: two full group barriers (here and before the aggregation).  Everything else is
+    // point to point -- each warp announces its part of an A operand on an mbarrier that only the MMA-issuing warp
+    // waits for, every warp gathers exactly the Psrc rows it will read itself (warp-local visibility), and the two
+    // column halves of a row exchange their LayerNorm statistics through a 64-thread named barrier.
     cp_async_wait<0>();
     wg_barrier(wg);
     const bool valid = r < ne;
     const int dn = valid ? W.dst[buf][r] : 0;
-    double rx = 0.0, ry = 0.0, rz = 0.0;
     {
       float a1v[24];  // half 0: he[0..23];  half 1: he[24..26], 15 RBFs, 6 zeros
       mbar_wait(&S.he_bar[wg], he_phase);
@@ -199,10 +212,14 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
 #pragma unroll
         for (int k = 0; k < 24; ++k) a1v[k] = valid ? hrow[k] : 0.f;
       } else {
+        double rx = 0.0, ry = 0.0, rz = 0.0;
         if (valid) {  // u_sub_v :204-205
           rx = W.xs[r * 6 + 0] - W.xs[r * 6 + 3];
           ry = W.xs[r * 6 + 1] - W.xs[r * 6 + 4];
           rz = W.xs[r * 6 + 2] - W.xs[r * 6 + 5];
+          W.xm[r * 3 + 0] = rx;
+          W.xm[r * 3 + 1] = ry;
+          W.xm[r * 3 + 2] = rz;
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) a1v[k] = valid ? hrow[24 + k] : 0.f;
@@ -229,9 +246,12 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    wg_barrier(wg);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.a_bar[wg]);
     // ---- GEMM1: [he|rbf] (K=48) x W1e ---------------------------------------------------------------
     if (issuer_warp) {
+      mbar_wait(&S.a_bar[wg_u], a_phase);   // all 8 warps' A columns are in TMEM (and they are done with the he staging)
+      a_phase ^= 1;
       tc_fence_after();
       if (elect_one()) {
         issue_gemm(tmem_wg, tmem_wg + 128, 32, w_saddr, TC_W1_SPLIT, 3);
@@ -239,21 +259,16 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
       }
       __syncwarp();
     }
-    // gathers of the node projections into smem (coalesced 16B chunks, 16 lanes per row): issued behind GEMM1,
-    // which they overlap -- they are first needed by epilogue 1
+    // Psrc[src] of MY warp's 32 rows x MY column half -> smem (8 lanes per row: 128 contiguous bytes), behind GEMM1
 #pragma unroll
-    for (int idx = q; idx < EQD_TM * 16; idx += 256) {
-      int row = idx >> 4, c4 = idx & 15;
-      bool ok = row < ne;
-      int s_row = ok ? W.src[buf][row] : 0;
-      cp_async16(&W.stage[row * TC_LD + c4 * 4], proj + (long)s_row * pw + c4 * 4, ok);
-    }
-    for (int idx = q; idx < nn * 16; idx += 256) {
-      int row = idx >> 4, c4 = idx & 15;
-      cp_async16(&W.pdst[row * TC_LD + c4 * 4], proj + (long)(n0 + row) * pw + 64 + c4 * 4, true);
+    for (int i = 0; i < 8; ++i) {
+      const int grow = wrow0 + i * 4 + (lane >> 3);
+      const bool ok = grow < ne;
+      const int s_row = ok ? W.src[buf][grow] : 0;
+      cp_async16(&W.stage[grow * TC_LD + half * 32 + (lane & 7) * 4], proj + (long)s_row * pw + half * 32 + (lane & 7) * 4, ok);
     }
     cp_async_commit();
-    // he staging and the other index buffer are free now: prefetch the next tile behind the MMAs
+    // he staging and the other index / Pdst buffers are free now: prefetch the next tile behind the MMAs
     if (has_next) prefetch(tile + tstride, buf ^ 1, e0n, nen, off_ln, n_ln, off_rn);
     mbar_wait(&S.mma_bar[wg], mma_phase);
     mma_phase ^= 1;
@@ -262,11 +277,11 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     {
       float v[32];
       tmem_ld32f(d_col, v);
-      if (has_next) cp_async_wait<1>(); else cp_async_wait<0>();  // gathers landed (the newest group is the prefetch)
-      wg_barrier(wg);
+      if (has_next) cp_async_wait<1>(); else cp_async_wait<0>();  // my gathers landed (the newest group is the prefetch)
+      __syncwarp();                                                  // ... and so did the rest of my warp's
       const int dloc = valid ? dn - n0 : 0;
       const float4* ps = reinterpret_cast<const float4*>(&W.stage[r * TC_LD + half * 32]);
-      const float4* pd = reinterpret_cast<const float4*>(&W.pdst[dloc * TC_LD + half * 32]);
+      const float4* pd = reinterpret_cast<const float4*>(&W.pdst[buf][dloc * TC_LD + half * 32]);
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) {
@@ -288,7 +303,7 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
       float* redf = reinterpret_cast<float*>(W.red);
       redf[(r * 2 + half) * 2 + 0] = mh;
       redf[(r * 2 + half) * 2 + 1] = (q4[0] + q4[1]) + (q4[2] + q4[3]);
-      wg_barrier(wg);
+      pair_barrier(pair_id);   // only the warp that owns the other half of these 32 rows
       const float m0 = redf[r * 4 + 0], m1 = redf[r * 4 + 2];
       const float mean = 0.5f * (m0 + m1);
       const float dm = m0 - m1;
@@ -299,26 +314,32 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
       store_half_split3(a_col + half * 16, v);
     }
     tc_fence_before();
-    wg_barrier(wg);  // A operand complete; everyone is done with the Psrc staging (it becomes the msg tile)
-    // ---- GEMM2+3 as ONE N=128 GEMM on the same A operand ----------------------------------------------------
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.a_bar[wg]);
+    // ---- GEMM2 and GEMM3 on the same A operand ------------------------------------------------------------------
     // msg = W2 a1 + b2 (edge_mlp.4) and the coordinate MLP's hidden pre-activation W3 msg + b3 =
-    // (W3 W2) a1 + (W3 b2 + b3) are both linear in a1: the stacked panel [W2 ; W3 W2] gives them in one pass,
-    // which removes a bf16x3 split of msg, a TMEM store, an MMA phase and two barriers per tile.
+    // (W3 W2) a1 + (W3 b2 + b3) are both linear in a1: the stacked panel [W2 ; W3 W2] gives them from one A operand
+    // (no bf16x3 split of msg, no second TMEM store).  Issued as two N=64 halves with their own completion barriers so
+    // that the msg epilogue runs under the second half's MMAs.
     if (issuer_warp) {
+      mbar_wait(&S.a_bar[wg_u], a_phase);
+      a_phase ^= 1;
       tc_fence_after();
       if (elect_one()) {
         const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};
-        const unsigned idesc = umma_idesc(128, 0);
-        unsigned accum = 0;
 #pragma unroll
-        for (int pr = 0; pr < 6; ++pr)
+        for (int hn = 0; hn < 2; ++hn) {
+          unsigned accum = 0;
 #pragma unroll
-          for (int kb = 0; kb < 4; ++kb) {
-            umma_ts_i(tmem_wg, tmem_wg + 128 + pa[pr] * 32 + kb * 8,
-                      b_desc_ex(w_saddr + TC_W23_BASE + pb[pr] * TC_W23_SPLIT + kb * 4096, 2048, 128), idesc, accum);
-            accum = 1;
-          }
-        umma_commit(&S.mma_bar[wg_u]);
+          for (int pr = 0; pr < 6; ++pr)
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) {
+              umma_ts(tmem_wg + hn * 64, tmem_wg + 128 + pa[pr] * 32 + kb * 8,
+                      b_desc_ex(w_saddr + TC_W23_BASE + pb[pr] * TC_W23_SPLIT + kb * 4096 + hn * 1024, 2048, 128), accum);
+              accum = 1;
+            }
+          umma_commit(hn == 0 ? &S.mma_bar[wg_u] : &S.mma2_bar[wg_u]);
+        }
       }
       __syncwarp();
     }
@@ -327,12 +348,15 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     tc_fence_after();
     {
       float v[32];
-      tmem_ld32f(d_col, v);                       // msg half row
+      tmem_ld32f(d_col, v);                       // msg half row -> my own row of the (warp-private until now) tile
 #pragma unroll
       for (int c = 0; c < 32; ++c) v[c] += cst.b2[half * 32 + c];
       float4* ms = reinterpret_cast<float4*>(&W.stage[r * TC_LD + half * 32]);
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) ms[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+      mbar_wait(&S.mma2_bar[wg], mma2_phase);
+      mma2_phase ^= 1;
+      tc_fence_after();
       tmem_ld32f(d_col + 64, v);                  // coordinate-MLP hidden half row
       float ph4[4] = {0.f, 0.f, 0.f, 0.f};        // 4 independent chains; the two halves are combined in fp64
 #pragma unroll
@@ -342,13 +366,21 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     }
     cp_async_wait<0>();  // next tile's indices have landed (issued behind GEMM1)
     tc_fence_before();
-    wg_barrier(wg);
+    wg_barrier(wg);      // msg tile, phi halves, x_rel complete; next tile's indices visible
     if (has_next) prefetch_x(buf ^ 1, nen);  // its x[src], x[dst]: xs of this tile was consumed in S1
-    if (half == 1) {
-      const double ph = W.red[r * 2] + W.red[r * 2 + 1] + (double)p.b_coor2;
-      W.xm[r * 3 + 0] = rx * ph;  // x_rel * phi :264
-      W.xm[r * 3 + 1] = ry * ph;
-      W.xm[r * 3 + 2] = rz * ph;
+    for (int o = q; o < nn * 3; o += 256) {  // coordinate update :264, 274-277, 286-292
+      int nd = o / 3, comp = o - nd * 3;
+      int rs = W.rp[buf][nd] - e0, re = W.rp[buf][nd + 1] - e0;
+      double sum = 0.0;
+      for (int rr = rs; rr < re; ++rr) {
+        const double ph = W.red[rr * 2] + W.red[rr * 2 + 1] + (double)p.b_coor2;
+        sum += W.xm[rr * 3 + comp] * ph;  // x_rel * phi :264
+      }
+      int deg = re - rs;
+      double upd = deg > 0 ? sum / (double)deg : 0.0;
+      long gi = (long)(n0 + nd) * 3 + comp;
+      double eta = (double)p.x_connection_init;
+      x_out[gi] = eta * x_orig[gi] + (1.0 - eta) * x_in[gi] + upd;
     }
     {  // mean aggregation of msg at the destination nodes (:280-283): 4 threads per channel, each a run of nodes
       const int c = q & 63, part = q >> 6;
@@ -364,18 +396,6 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
         if (rr < re) s0 += col[rr * TC_LD];
         aggr[(long)(n0 + nd) * 64 + c] = re > rs ? (s0 + s1) / (float)(re - rs) : 0.f;
       }
-    }
-    wg_barrier(wg);
-    for (int o = q; o < nn * 3; o += 256) {  // :274-277, 286-292
-      int nd = o / 3, comp = o - nd * 3;
-      int rs = W.rp[buf][nd] - e0, re = W.rp[buf][nd + 1] - e0;
-      double sum = 0.0;
-      for (int rr = rs; rr < re; ++rr) sum += W.xm[rr * 3 + comp];
-      int deg = re - rs;
-      double upd = deg > 0 ? sum / (double)deg : 0.0;
-      long gi = (long)(n0 + nd) * 3 + comp;
-      double eta = (double)p.x_connection_init;
-      x_out[gi] = eta * x_orig[gi] + (1.0 - eta) * x_in[gi] + upd;
     }
     e0 = e0n; ne = nen; off_l = off_ln; n_l = n_ln; off_r = off_rn; buf ^= 1;
   }
