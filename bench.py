@@ -262,7 +262,8 @@ def run_engine(args, rank, local_rank, world):
     # ---- device-resident throughput ("value") -------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         model(dev_batch, 0)
-    timer = StageTimer(torch)
+    from equidock_public_b200 import engine as engine_mod
+    timer = StageTimer(torch) if engine_mod._PY_FORWARD else engine_mod.NativeStageTimer()
     orig_forward = IEGMNEngine.forward
     IEGMNEngine.forward = lambda self, *a, **k: orig_forward(self, *a, stage_timer=timer, **k)
     sampler = ClockSampler(local_rank)

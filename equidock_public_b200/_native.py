@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libeqd_iegmn.so')
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 EDGE_FEATS, N_RBF, HID, H0, H0_PAD, N_RES_TYPES, HEADS, TILE_ROWS = 27, 15, 64, 69, 72, 21, 50, 128
 STATUS_SVD_DEGENERATE, STATUS_NAN, STATUS_DEGREE_OVERFLOW = 1, 2, 4
 
@@ -37,6 +37,12 @@ class EqdLayerParams(C.Structure):
                 ('skip_weight_h', _f32), ('x_connection_init', _f32), ('leaky_slope', _f32)]
 
 
+class EqdForwardIO(C.Structure):
+    _fields_ = [(n, _vp) for n in ('emb', 'res_lig', 'res_rec', 'mu_lig', 'mu_rec', 'x_lig', 'x_rec', 'rot', 'trans',
+                                   'ligand_out', 'sing', 'status', 'h_out', 'x_out', 'keypts', 'cov', 'ymean', 'stage_events')] + \
+               [('layer0_fp32', _i32)]
+
+
 class EqdHeadParams(C.Structure):
     _fields_ = [('w_mean', _vp), ('b_mean', _vp), ('w_key', _vp), ('w_query', _vp), ('m_qk', _vp), ('leaky_slope', _f32)]
 
@@ -53,12 +59,21 @@ PROTOTYPES = {
     'eqd_node_stage': (C.c_int, [_G, _L, _L, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     'eqd_kv_blocks_bytes': (C.c_size_t, [_i32]),
     'eqd_project_tc': (C.c_int, [_G, _L, _vp, _vp, _vp, _vp]),
+    'eqd_project_tc0': (C.c_int, [_G, _L, _vp, _vp, _vp, _vp, _vp]),
+    'eqd_attention_tc0': (C.c_int, [_G, _vp, _vp, _vp, _vp, _vp]),
+    'eqd_node_mlp_tc0': (C.c_int, [_G, _L, _vp, _vp, _vp, _vp, _vp]),
+    'eqd_node_stage_tc0': (C.c_int, [_G, _L, _L, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'eqd_kv_blocks': (C.c_int, [_G, _vp, _i32, _i32, _i32, _vp, _vp]),
     'eqd_attention_tc': (C.c_int, [_G, _vp, _vp, _vp, _vp]),
     'eqd_node_mlp_tc': (C.c_int, [_G, _L, _vp, _vp, _vp, _vp, _vp, _vp]),
     'eqd_node_stage_tc': (C.c_int, [_G, _L, _L, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'eqd_iegmn_layer_forward': (C.c_int, [_G, _L, _L, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'eqd_head_fold': (C.c_int, [_H, _vp, _vp]),
+    'eqd_forward_workspace_bytes': (C.c_size_t, [_G]),
+    'eqd_iegmn_forward': (C.c_int, [_G, C.POINTER(_L), _i32, _H, C.POINTER(EqdForwardIO), _vp, C.c_size_t, _vp]),
+    'eqd_event_create': (_vp, []),
+    'eqd_event_destroy': (None, [_vp]),
+    'eqd_event_elapsed_ms': (C.c_float, [_vp, _vp]),
     'eqd_keypoints': (C.c_int, [_G, _H, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
     'eqd_kabsch_apply': (C.c_int, [_G, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

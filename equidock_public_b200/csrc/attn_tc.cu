@@ -17,24 +17,33 @@ namespace eqd {
 #define AT_KEYS 64            // keys per chunk = 8 blocks
 #define AT_CHUNK_BYTES 8192   // per split
 
+// X5 = the 69-wide layer 0: the tensor cores handle channels 0..63 exactly as in a 64-wide layer; channels 64..68 of
+// Q, K, V (fp32 in x5[n][16] = [K64..67 | V64..67 | K68 V68 | Q64..68 | 0], written by the layer-0 projection) are a
+// rank-5 update of the scores and five extra output columns, done with plain FMAs next to the exp().
+template <bool X5>
 struct AtGroupSmem {
   unsigned char k[2][3][AT_CHUNK_BYTES];  // double-buffered K chunks (3 splits)
   unsigned char v[2][3][AT_CHUNK_BYTES];
   float red[EQD_TM * 2];
+  float x5c[X5 ? 2 : 1][X5 ? AT_KEYS * 16 : 4];   // x5 rows of the K chunk in flight (same double buffering as k)
+  float red5[X5 ? EQD_TM * 2 * 5 : 4];
 };
+template <bool X5>
 struct AtSmem {
-  AtGroupSmem grp[2];
+  AtGroupSmem<X5> grp[2];
   unsigned long long k_bar[2][2], v_bar[2][2], mma_bar[2];
   unsigned int tmem_base;
 };
 
+template <bool X5>
 __global__ void __launch_bounds__(AT_THREADS, 1)
-attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, const unsigned char* __restrict__ kv, long kv_split_stride,
-                    float* __restrict__ mu) {
+attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const unsigned char* __restrict__ kv,
+                    long kv_split_stride, const float* __restrict__ x5, float* __restrict__ mu, int ldmu) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  AtSmem& S = *reinterpret_cast<AtSmem*>(smem_raw);
+  AtSmem<X5>& S = *reinterpret_cast<AtSmem<X5>*>(smem_raw);
   const int tid = threadIdx.x, wg = tid >> 8, q = tid & 255, half = q >> 7, r = q & 127, warp = tid >> 5;
-  AtGroupSmem& G = S.grp[wg];
+  AtGroupSmem<X5>& G = S.grp[wg];
+  TRACE_START(1);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -64,11 +73,25 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, const unsigned 
   const unsigned char* k_g = kv;                              // which = 0
   const unsigned char* v_g = kv + 3 * kv_split_stride;        // which = 1
 
-  auto load_chunk = [&](const unsigned char* src, unsigned char (*dst)[AT_CHUNK_BYTES], unsigned long long* bar, int blk0) {
+  // a chunk of K or V blocks; x5buf >= 0: also the fp32 x5 rows of those 64 keys (they travel with the K chunks)
+  auto load_chunk = [&](const unsigned char* src, unsigned char (*dst)[AT_CHUNK_BYTES], unsigned long long* bar, int blk0,
+                        int x5buf) {
     if (q == 0) {
-      mbar_expect_tx(bar, 3 * AT_CHUNK_BYTES);
+      const bool with5 = X5 && x5buf >= 0;
+      mbar_expect_tx(bar, 3 * AT_CHUNK_BYTES + (with5 ? AT_KEYS * 64 : 0));
 #pragma unroll
       for (int s = 0; s < 3; ++s) bulk_g2s(dst[s], src + s * kv_split_stride + (long)blk0 * 1024, AT_CHUNK_BYTES, bar);
+      if (with5) bulk_g2s(G.x5c[x5buf], x5 + (long)blk0 * 8 * 16, AT_KEYS * 64, bar);
+    }
+  };
+  // s[i] += <Q5, K5[key i of my half]>   (keys are uniform across the warp: broadcast shared loads)
+  auto add_s5 = [&](float (&s)[32], const float* xc, const float (&q5)[5]) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float* row = xc + (half * 32 + i) * 16;
+      const float4 k4 = *reinterpret_cast<const float4*>(row);
+      const float k8 = row[8];
+      s[i] += q5[0] * k4.x + q5[1] * k4.y + q5[2] * k4.z + q5[3] * k4.w + q5[4] * k8;
     }
   };
   // S = Q K^T for one 64-key chunk in K buffer `kb_`.  hi_only: just the leading bf16 x bf16 product (4 MMAs instead
@@ -123,6 +146,7 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, const unsigned 
   };
 
   for (int tile = blockIdx.x * 2 + wg; tile < g.n_node_tiles; tile += gridDim.x * 2) {
+    if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, tile, 1);
     const int seg = g.node_tiles[2 * tile], node0 = g.node_tiles[2 * tile + 1];
     const int nvalid = min(EQD_TM, g.seg_ptr[seg + 1] - node0);
     const int pseg = seg < B ? seg + B : seg - B;
@@ -131,10 +155,15 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, const unsigned 
     const int nchunks = (blk_hi - blk_lo + 7) >> 3;
     const int node = node0 + r;
     const bool valid = r < nvalid;
-    if (nchunks > 0) load_chunk(k_g, G.k[0], &S.k_bar[wg][0], blk_lo);
+    if (nchunks > 0) load_chunk(k_g, G.k[0], &S.k_bar[wg][0], blk_lo, 0);
+    float q5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (X5 && valid) {
+#pragma unroll
+      for (int e = 0; e < 5; ++e) q5[e] = x5[(long)node * 16 + 10 + e];
+    }
     {  // Q row -> bf16x3 -> TMEM
       float v[32];
-      const float4* sp = reinterpret_cast<const float4*>(proj + (long)node * 320 + 128 + half * 32);
+      const float4* sp = reinterpret_cast<const float4*>(proj + (long)node * pw + 128 + half * 32);
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) {
         float4 t = valid ? sp[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -152,11 +181,12 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, const unsigned 
       kph[kb_] ^= 1;
       issue_s(kb_, true);
       // the other K buffer was last read by the S GEMM of chunk c-1, already waited for: prefetch into it
-      if (c + 1 < nchunks) load_chunk(k_g, G.k[kb_ ^ 1], &S.k_bar[wg][kb_ ^ 1], blk_lo + 8 * (c + 1));
-      else load_chunk(k_g, G.k[kb_ ^ 1], &S.k_bar[wg][kb_ ^ 1], blk_lo);   // first chunk of pass 2
+      if (c + 1 < nchunks) load_chunk(k_g, G.k[kb_ ^ 1], &S.k_bar[wg][kb_ ^ 1], blk_lo + 8 * (c + 1), kb_ ^ 1);
+      else load_chunk(k_g, G.k[kb_ ^ 1], &S.k_bar[wg][kb_ ^ 1], blk_lo, kb_ ^ 1);   // first chunk of pass 2
       wait_mma();
       float s[32];
       tmem_ld32f(tmem + 96 + half * 32, s);
+      if (X5) add_s5(s, G.x5c[kb_], q5);
       const int key0 = (blk_lo + 8 * c) * 8 + half * 32;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -174,19 +204,21 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, const unsigned 
     float o_acc[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
-    if (nchunks > 0) load_chunk(v_g, G.v[0], &S.v_bar[wg][0], blk_lo);
+    if (nchunks > 0) load_chunk(v_g, G.v[0], &S.v_bar[wg][0], blk_lo, -1);
+    float o5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     for (int c = 0; c < nchunks; ++c) {
       const int kb_ = (nchunks + c) & 1, vb_ = c & 1;   // K buffers keep alternating after pass 1
       mbar_wait(&S.k_bar[wg][kb_], kph[kb_]);
       kph[kb_] ^= 1;
       issue_s(kb_, false);
       if (c + 1 < nchunks) {
-        load_chunk(k_g, G.k[kb_ ^ 1], &S.k_bar[wg][kb_ ^ 1], blk_lo + 8 * (c + 1));
-        load_chunk(v_g, G.v[vb_ ^ 1], &S.v_bar[wg][vb_ ^ 1], blk_lo + 8 * (c + 1));   // its last reader (P V of c-1) is done
+        load_chunk(k_g, G.k[kb_ ^ 1], &S.k_bar[wg][kb_ ^ 1], blk_lo + 8 * (c + 1), kb_ ^ 1);
+        load_chunk(v_g, G.v[vb_ ^ 1], &S.v_bar[wg][vb_ ^ 1], blk_lo + 8 * (c + 1), -1);   // its last reader (P V of c-1) is done
       }
       wait_mma();
       float s[32];
       tmem_ld32f(tmem + 96 + half * 32, s);
+      if (X5) add_s5(s, G.x5c[kb_], q5);
       const int key0 = (blk_lo + 8 * c) * 8 + half * 32;
       float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -195,6 +227,15 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, const unsigned 
         float pj = (kn >= j0 && kn < j1) ? expf(s[i] - mx) : 0.f;
         s[i] = pj;
         l4[i & 3] += pj;
+        if (X5) {   // the five extra output columns: o5 += p V5[key]
+          const float* row = G.x5c[kb_] + (half * 32 + i) * 16;
+          const float4 v4 = *reinterpret_cast<const float4*>(row + 4);
+          o5[0] = fmaf(pj, v4.x, o5[0]);
+          o5[1] = fmaf(pj, v4.y, o5[1]);
+          o5[2] = fmaf(pj, v4.z, o5[2]);
+          o5[3] = fmaf(pj, v4.w, o5[3]);
+          o5[4] = fmaf(pj, row[9], o5[4]);
+        }
       }
       l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
       tc_fence_before();
@@ -218,12 +259,25 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, const unsigned 
     }
     // ---------------- mu = O / l -----------------------------------------------------------------------------
     G.red[r * 2 + half] = l;
+    if (X5) {
+#pragma unroll
+      for (int e = 0; e < 5; ++e) G.red5[(r * 2 + half) * 5 + e] = o5[e];
+    }
     wg_barrier(wg);
     l = G.red[r * 2] + G.red[r * 2 + 1];
     {
       const float inv = l > 0.f ? 1.f / l : 0.f;
+      if (X5 && valid && half == 0) {   // mu[64..68], then zeros up to the row stride
+        float e8[8];
+#pragma unroll
+        for (int e = 0; e < 5; ++e) e8[e] = (G.red5[r * 10 + e] + G.red5[r * 10 + 5 + e]) * inv;
+        e8[5] = e8[6] = e8[7] = 0.f;
+        float4* de = reinterpret_cast<float4*>(mu + (long)node * ldmu + 64);
+        de[0] = make_float4(e8[0], e8[1], e8[2], e8[3]);
+        de[1] = make_float4(e8[4], e8[5], e8[6], e8[7]);
+      }
       if (valid) {
-        float4* dst = reinterpret_cast<float4*>(mu + (long)node * EQD_HID + half * 32);
+        float4* dst = reinterpret_cast<float4*>(mu + (long)node * ldmu + half * 32);
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4)
           dst[c4] = make_float4(o_acc[c4 * 4] * inv, o_acc[c4 * 4 + 1] * inv, o_acc[c4 * 4 + 2] * inv, o_acc[c4 * 4 + 3] * inv);
@@ -234,22 +288,41 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, const unsigned 
   }
   tc_fence_before();
   __syncthreads();
+  TRACE_END(1);
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base), "r"(512));
 }
 
 }  // namespace eqd
 
-extern "C" int eqd_attention_tc(const eqd_graph* g, const float* proj, const void* kv, float* mu, void* stream) {
-  if (!g || !proj || !kv || !mu) return EQD_ERR_BAD_ARG;
+EQD_TRACE_SETTER(eqd_trace_set_attn)
+
+template <bool X5>
+static int launch_attention_tc(const eqd_graph* g, const float* proj, int pw, const void* kv, const float* x5, float* mu,
+                               int ldmu, void* stream) {
+  eqd_set_fence_stream(stream);
   if (reinterpret_cast<uintptr_t>(kv) & 15) return EQD_ERR_BAD_ARG;
   if (g->n_node_tiles <= 0) return EQD_OK;
-  size_t smem = sizeof(eqd::AtSmem) + 128;
-  cudaFuncSetAttribute(eqd::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  size_t smem = sizeof(eqd::AtSmem<X5>) + 128;
+  cudaFuncSetAttribute(eqd::attention_tc_kernel<X5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int grid = (g->n_node_tiles + 1) / 2;
   if (grid > 148) grid = 148;
   long split_stride = (long)((g->n_nodes + 7) / 8 + 8) * 1024;
-  eqd::attention_tc_kernel<<<grid, AT_THREADS, smem, (cudaStream_t)stream>>>(*g, proj, reinterpret_cast<const unsigned char*>(kv),
-                                                                            split_stride, mu);
+  eqd::attention_tc_kernel<X5><<<grid, AT_THREADS, smem, (cudaStream_t)stream>>>(
+      *g, proj, pw, reinterpret_cast<const unsigned char*>(kv), split_stride, x5, mu, ldmu);
   EQD_CUDA_LAUNCH_CHECK();
   return EQD_OK;
+}
+
+extern "C" int eqd_attention_tc(const eqd_graph* g, const float* proj, const void* kv, float* mu, void* stream) {
+  eqd_set_fence_stream(stream);
+  if (!g || !proj || !kv || !mu) return EQD_ERR_BAD_ARG;
+  return launch_attention_tc<false>(g, proj, 320, kv, nullptr, mu, EQD_HID, stream);
+}
+
+extern "C" int eqd_attention_tc0(const eqd_graph* g, const float* proj, const void* kv, const float* x5, float* mu,
+                                 void* stream) {
+  eqd_set_fence_stream(stream);
+  if (!g || !proj || !kv || !x5 || !mu) return EQD_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(x5) & 15) return EQD_ERR_BAD_ARG;
+  return launch_attention_tc<true>(g, proj, 128 + 3 * 72, kv, x5, mu, EQD_H0_PAD, stream);
 }

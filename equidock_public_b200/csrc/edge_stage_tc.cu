@@ -66,6 +66,7 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
   const int ntiles = (g.n_nodes + tn - 1) / tn;
   const float slope = p.leaky_slope;
 
+  TRACE_START(0);
   // ---- one-time setup: TMEM, barriers, weights (one TMA bulk copy) -------------------------------
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
@@ -98,6 +99,7 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
   const unsigned tmem = tmem_wg + ((unsigned)((warp & 3) * 32) << 16);           // my lane quarter
   const unsigned d_col = tmem + half * 32;                                         // my half of D (64 columns)
   const unsigned a_col = tmem + 128;                                               // A: 3 splits x 32 columns (D: 0..127)
+  if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, 0, 1);
   mbar_wait(&S.w_bar, 0);
   unsigned mma_phase = 0, mma2_phase = 0, he_phase = 0, a_phase = 0;
   const unsigned w_saddr = smem_u32(S.w);
@@ -199,14 +201,17 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     // point to point -- each warp announces its part of an A operand on an mbarrier that only the MMA-issuing warp
     // waits for, every warp gathers exactly the Psrc rows it will read itself (warp-local visibility), and the two
     // column halves of a row exchange their LayerNorm statistics through a 64-thread named barrier.
+    if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, tile, 2);
     cp_async_wait<0>();
     wg_barrier(wg);
+    if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, tile, 3);
     const bool valid = r < ne;
     const int dn = valid ? W.dst[buf][r] : 0;
     {
       float a1v[24];  // half 0: he[0..23];  half 1: he[24..26], 15 RBFs, 6 zeros
       mbar_wait(&S.he_bar[wg], he_phase);
       he_phase ^= 1;
+      if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, tile, 4);
       const float* hrow = W.he + (r < n_l ? off_l + r * EQD_EDGE_FEATS : off_r + (r - n_l) * EQD_EDGE_FEATS);
       if (half == 0) {
 #pragma unroll
@@ -250,8 +255,10 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     if (lane == 0) mbar_arrive(&S.a_bar[wg]);
     // ---- GEMM1: [he|rbf] (K=48) x W1e ---------------------------------------------------------------
     if (issuer_warp) {
+      if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, tile, 5);
       mbar_wait(&S.a_bar[wg_u], a_phase);   // all 8 warps' A columns are in TMEM (and they are done with the he staging)
       a_phase ^= 1;
+      if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, tile, 6);
       tc_fence_after();
       if (elect_one()) {
         issue_gemm(tmem_wg, tmem_wg + 128, 32, w_saddr, TC_W1_SPLIT, 3);
@@ -270,9 +277,11 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     cp_async_commit();
     // he staging and the other index / Pdst buffers are free now: prefetch the next tile behind the MMAs
     if (has_next) prefetch(tile + tstride, buf ^ 1, e0n, nen, off_ln, n_ln, off_rn);
+    if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, tile, 7);
     mbar_wait(&S.mma_bar[wg], mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
+    if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, tile, 8);
     // ---- epilogue 1: + Psrc[src] + Pdst[dst], LeakyReLU, LayerNorm -> bf16x3 -> TMEM ----------------
     {
       float v[32];
@@ -303,6 +312,7 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
       float* redf = reinterpret_cast<float*>(W.red);
       redf[(r * 2 + half) * 2 + 0] = mh;
       redf[(r * 2 + half) * 2 + 1] = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+      if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, tile, 9);
       pair_barrier(pair_id);   // only the warp that owns the other half of these 32 rows
       const float m0 = redf[r * 4 + 0], m1 = redf[r * 4 + 2];
       const float mean = 0.5f * (m0 + m1);
@@ -322,9 +332,11 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     // (no bf16x3 split of msg, no second TMEM store).  Issued as two N=64 halves with their own completion barriers so
     // that the msg epilogue runs under the second half's MMAs.
     if (issuer_warp) {
+      if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, tile, 10);
       mbar_wait(&S.a_bar[wg_u], a_phase);
       a_phase ^= 1;
       tc_fence_after();
+      if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, tile, 11);
       if (elect_one()) {
         const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};
 #pragma unroll
@@ -343,9 +355,11 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
       }
       __syncwarp();
     }
+    if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, tile, 12);
     mbar_wait(&S.mma_bar[wg], mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
+    if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, tile, 13);
     {
       float v[32];
       tmem_ld32f(d_col, v);                       // msg half row -> my own row of the (warp-private until now) tile
@@ -356,6 +370,7 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
       for (int c4 = 0; c4 < 8; ++c4) ms[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
       mbar_wait(&S.mma2_bar[wg], mma2_phase);
       mma2_phase ^= 1;
+      if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, tile, 14);
       tc_fence_after();
       tmem_ld32f(d_col + 64, v);                  // coordinate-MLP hidden half row
       float ph4[4] = {0.f, 0.f, 0.f, 0.f};        // 4 independent chains; the two halves are combined in fp64
@@ -367,6 +382,7 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     cp_async_wait<0>();  // next tile's indices have landed (issued behind GEMM1)
     tc_fence_before();
     wg_barrier(wg);      // msg tile, phi halves, x_rel complete; next tile's indices visible
+    if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, tile, 15);
     if (has_next) prefetch_x(buf ^ 1, nen);  // its x[src], x[dst]: xs of this tile was consumed in S1
     for (int o = q; o < nn * 3; o += 256) {  // coordinate update :264, 274-277, 286-292
       int nd = o / 3, comp = o - nd * 3;
@@ -399,16 +415,21 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     }
     e0 = e0n; ne = nen; off_l = off_ln; n_l = n_ln; off_r = off_rn; buf ^= 1;
   }
+  if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, 0xffff, 16);
   cp_async_wait<0>();
   tc_fence_before();
   __syncthreads();
+  TRACE_END(0);
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base), "r"(512));
 }
 
 }  // namespace eqd
 
+EQD_TRACE_SETTER(eqd_trace_set_edge)
+
 extern "C" int eqd_edge_stage(const eqd_graph* g, const eqd_layer_params* p, const float* proj, const double* x_in,
                               const double* x_orig, float* aggr, double* x_out, int32_t* status, void* stream) {
+  eqd_set_fence_stream(stream);
   if (!g || !p || !proj || !x_in || !x_orig || !aggr || !x_out || !status) return EQD_ERR_BAD_ARG;
   if (!p->w_edge_tc || !p->edge_consts_host) return EQD_ERR_BAD_ARG;
   if (g->max_in_degree < 1 || g->max_in_degree > EQD_TM) return EQD_ERR_UNSUPPORTED;

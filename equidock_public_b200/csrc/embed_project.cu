@@ -8,6 +8,7 @@ __global__ void embed_kernel(eqd_graph g, const float* __restrict__ emb, const f
                              const float* __restrict__ res_r, const float* __restrict__ mu_l,
                              const float* __restrict__ mu_r, const float* __restrict__ x_l,
                              const float* __restrict__ x_r, float* __restrict__ h0, double* __restrict__ x64) {
+  TRACE_START(4);
   const int per_node = EQD_H0_PAD / 4;  // 18 float4 per node
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   long total = (long)g.n_nodes * per_node;
@@ -62,9 +63,12 @@ __global__ void __launch_bounds__(EQD_THREADS) project_kernel(eqd_graph g, eqd_l
 
 }  // namespace eqd
 
+EQD_TRACE_SETTER(eqd_trace_set_embed)
+
 extern "C" int eqd_embed(const eqd_graph* g, const float* emb, const float* res_feat_lig, const float* res_feat_rec,
                          const float* mu_lig, const float* mu_rec, const float* x_lig, const float* x_rec, float* h0,
                          double* x64, void* stream) {
+  eqd_set_fence_stream(stream);
   if (!g || !emb || !h0 || !x64) return EQD_ERR_BAD_ARG;
   if (g->n_nodes <= 0) return EQD_OK;
   long total = (long)g->n_nodes * (EQD_H0_PAD / 4);
@@ -78,6 +82,7 @@ extern "C" int eqd_embed(const eqd_graph* g, const float* emb, const float* res_
 
 extern "C" int eqd_project(const eqd_graph* g, const eqd_layer_params* p, const float* h, int32_t ldh, float* proj,
                            void* stream) {
+  eqd_set_fence_stream(stream);
   if (!g || !p || !h || !proj) return EQD_ERR_BAD_ARG;
   if (!((p->dh == 64 && p->dhp == 64) || (p->dh == 69 && p->dhp == 72))) return EQD_ERR_UNSUPPORTED;
   if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)

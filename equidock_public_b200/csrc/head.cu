@@ -6,6 +6,8 @@
 // Algebra: the reference materialises keys (n x 3200) and compares them with the 3200-d query;
 //   logits[k][j] = <W_K,k h_j , W_Q,k qbar> / sqrt(64) = h_j . u_k,   u_k = W_K,k^T (W_Q,k qbar) / 8
 // so only u (50 x 64) is formed -- 20x fewer FLOPs, same value up to rounding.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace eqd {
@@ -18,6 +20,7 @@ namespace eqd {
 // ---- partial column sums of LeakyReLU(W_m h + b_m) over each node tile (:525, :529) -------------
 __global__ void __launch_bounds__(EQD_THREADS, 2)
 head_mean_kernel(eqd_graph g, eqd_head_params hp, const float* __restrict__ h, float* __restrict__ part) {
+  TRACE_START(5);
   extern __shared__ __align__(16) float smem[];
   constexpr int LD = 68;
   float* A = smem;                   // [128][68]
@@ -151,6 +154,7 @@ struct KeypSmem {
 __global__ void __launch_bounds__(KP_THREADS, 4)
 keypoints_kernel(eqd_graph g, const float* __restrict__ h, const double* __restrict__ x,
                  const double* __restrict__ u_all /* [2B][50][64] */, double* __restrict__ keypts) {
+  TRACE_START(6);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KeypSmem& s = *reinterpret_cast<KeypSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -358,6 +362,7 @@ __global__ void kabsch_apply_kernel(eqd_graph g, const double* __restrict__ cov,
                                     const float* __restrict__ x_lig_in, const int* __restrict__ pair_mask,
                                     float* __restrict__ rot, float* __restrict__ trans, float* __restrict__ ligand_out,
                                     double* __restrict__ sing, int* __restrict__ status) {
+  TRACE_START(7);
   const int b = blockIdx.x;
   if (pair_mask && pair_mask[b] == 0) return;
   __shared__ double Tb[12];
@@ -433,9 +438,28 @@ __global__ void tile_ptr_kernel(eqd_graph g, int* __restrict__ tile_ptr) {
 
 }  // namespace eqd
 
+EQD_TRACE_SETTER(eqd_trace_set_head)
+
 static inline size_t eqd_align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 extern "C" int eqd_abi_version(void) { return EQD_ABI_VERSION; }
+
+// ---- launch fence (see common.cuh) ---------------------------------------------------------------------------------
+static thread_local cudaStream_t g_fence_stream = nullptr;
+extern "C" void eqd_set_fence_stream(void* stream) { g_fence_stream = (cudaStream_t)stream; }
+void eqd_launch_fence() {
+  static const bool enabled = !(getenv("EQD_LAUNCH_FENCE") && atoi(getenv("EQD_LAUNCH_FENCE")) == 0);
+  if (!enabled) return;
+  static thread_local cudaEvent_t ev = nullptr;
+  static thread_local int ev_device = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (ev == nullptr || ev_device != dev) {
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; return; }
+    ev_device = dev;
+  }
+  cudaEventRecord(ev, g_fence_stream);
+}
 
 static inline size_t ws_part_bytes(int32_t n_node_tiles) { return eqd_align256((size_t)(n_node_tiles > 0 ? n_node_tiles : 1) * 64 * sizeof(float)); }
 static inline size_t ws_tile_ptr_bytes(int32_t n_pairs) { return eqd_align256((size_t)(2 * (n_pairs > 0 ? n_pairs : 0) + 1) * sizeof(int)); }
@@ -449,6 +473,7 @@ extern "C" size_t eqd_workspace_bytes(int32_t n_nodes, int32_t n_node_tiles, int
 }
 
 extern "C" int eqd_head_fold(const eqd_head_params* hp, double* m_qk, void* stream) {
+  eqd_set_fence_stream(stream);
   if (!hp || !hp->w_key || !hp->w_query || !m_qk) return EQD_ERR_BAD_ARG;
   eqd::head_fold_kernel<<<EQD_HEADS, 256, 0, (cudaStream_t)stream>>>(*hp, m_qk);
   EQD_CUDA_LAUNCH_CHECK();
@@ -458,6 +483,7 @@ extern "C" int eqd_head_fold(const eqd_head_params* hp, double* m_qk, void* stre
 extern "C" int eqd_keypoints(const eqd_graph* g, const eqd_head_params* hp, const float* h, const double* x,
                              void* workspace, size_t workspace_bytes, double* keypts, double* ymean, double* cov,
                              void* stream) {
+  eqd_set_fence_stream(stream);
   if (!g || !hp || !h || !x || !workspace || !keypts || !ymean || !cov) return EQD_ERR_BAD_ARG;
   if (!hp->m_qk || (reinterpret_cast<uintptr_t>(hp->m_qk) & 15)) return EQD_ERR_BAD_ARG;   // eqd_head_fold() output
   if (workspace_bytes < eqd_workspace_bytes(g->n_nodes, g->n_node_tiles, g->n_pairs)) return EQD_ERR_WORKSPACE;
@@ -505,6 +531,7 @@ extern "C" int eqd_keypoints(const eqd_graph* g, const eqd_head_params* hp, cons
 extern "C" int eqd_kabsch_apply(const eqd_graph* g, const double* cov, const double* ymean, const float* x_lig_in,
                                 const int32_t* pair_mask, float* rot, float* trans, float* ligand_out, double* sing,
                                 int32_t* status, void* stream) {
+  eqd_set_fence_stream(stream);
   if (!g || !cov || !ymean || !x_lig_in || !rot || !trans || !ligand_out || !sing || !status) return EQD_ERR_BAD_ARG;
   if (g->n_pairs <= 0) return EQD_OK;
   eqd::kabsch_apply_kernel<<<g->n_pairs, 128, 0, (cudaStream_t)stream>>>(*g, cov, ymean, x_lig_in, pair_mask, rot,

@@ -98,6 +98,21 @@ __device__ __forceinline__ void issue_gemm(unsigned d_tmem, unsigned a_base, uns
       accum = 1;
     }
 }
+// Same for a K-major [N][K] panel of any N (multiple of 16): a k-block of 16 is 32 N bytes, LBO = 16 N, SBO = 128.
+template <int N>
+__device__ __forceinline__ void issue_gemm_n(unsigned d_tmem, unsigned a_base, unsigned a_split_cols, unsigned w_saddr,
+                                             unsigned w_split_bytes, int kblocks, unsigned accum0 = 0) {
+  const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};
+  const unsigned idesc = umma_idesc(N, 0);
+  unsigned accum = accum0;
+#pragma unroll
+  for (int pr = 0; pr < 6; ++pr)
+    for (int kb = 0; kb < kblocks; ++kb) {
+      umma_ts_i(d_tmem, a_base + pa[pr] * a_split_cols + kb * 8,
+                b_desc_ex(w_saddr + pb[pr] * w_split_bytes + kb * (N * 32), N * 16, 128), idesc, accum);
+      accum = 1;
+    }
+}
 __device__ __forceinline__ bool elect_one() {
   unsigned pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -142,14 +157,38 @@ __device__ __forceinline__ void tmem_ld32_nowait(unsigned taddr, unsigned (&r)[3
       : "r"(taddr) : "memory");
 }
 // 32 fp32 values (this thread's half of its row) -> bf16x3 -> TMEM: split s lands at a_taddr + 32*s, 16 columns
-__device__ __forceinline__ void store_half_split3(unsigned a_taddr, const float (&v)[32]) {
+// (split_cols: columns between consecutive splits of the A operand, 32 for a 64-wide K, 40 for K = 80)
+__device__ __forceinline__ void store_half_split3(unsigned a_taddr, const float (&v)[32], unsigned split_cols = 32) {
   unsigned p0[16], p1[16], p2[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) split3_pair(v[2 * c], v[2 * c + 1], p0[c], p1[c], p2[c]);
   tmem_st16(a_taddr, p0);
-  tmem_st16(a_taddr + 32, p1);
-  tmem_st16(a_taddr + 64, p2);
+  tmem_st16(a_taddr + split_cols, p1);
+  tmem_st16(a_taddr + 2 * split_cols, p2);
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// 8 fp32 values + 8 zeros (one K block of 16) -> bf16x3 -> 8 TMEM columns per split
+__device__ __forceinline__ void store_extra8_split3(unsigned a_taddr, const float (&t)[8], unsigned split_cols) {
+  unsigned p0[8], p1[8], p2[8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) split3_pair(t[2 * c], t[2 * c + 1], p0[c], p1[c], p2[c]);
+#pragma unroll
+  for (int c = 4; c < 8; ++c) p0[c] = p1[c] = p2[c] = 0u;
+  tmem_st8(a_taddr, p0);
+  tmem_st8(a_taddr + split_cols, p1);
+  tmem_st8(a_taddr + 2 * split_cols, p2);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16f(unsigned taddr, float (&v)[16]) {
+  unsigned a[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]), "=r"(a[9]),
+        "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(a[i]);
 }
 __device__ __forceinline__ void tmem_st4(unsigned taddr, const unsigned* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),

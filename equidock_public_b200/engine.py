@@ -36,6 +36,12 @@ def umma_bf16x3(w: torch.Tensor) -> torch.Tensor:
     return torch.cat(out)
 
 
+# EQD_LAYER0_FFMA=1 keeps the 69-wide layer 0 on the fp32 CUDA-core kernels (A/B comparisons)
+_LAYER0_FFMA = bool(int(__import__('os').environ.get('EQD_LAYER0_FFMA', '0')))
+# EQD_PY_FORWARD=1: drive the stages one C call at a time from Python instead of through eqd_iegmn_forward
+_PY_FORWARD = bool(int(__import__('os').environ.get('EQD_PY_FORWARD', '1')))
+
+
 class PackedLayer:
     """One IEGMN_Layer's parameters repacked k-major for the kernels (see eqd_layer_params)."""
 
@@ -94,6 +100,23 @@ class PackedLayer:
             assert tc['w_node_tc'].numel() * 2 == 129024 and tc['w_proj_tc'].numel() * 2 == 122880
             self.node_consts_host = torch.stack([b5, f('node_mlp.3.weight'), f('node_mlp.3.bias'), b6]).cpu().contiguous()
             self.proj_bias_host = b_proj.cpu().contiguous()
+        else:  # layer 0 (69 wide, h = h0): K padded to 80; channels 64..68 of Q / K / V form a sixth N = 16 group
+            p80 = lambda w: torch.cat([w, z(w.shape[0], 80 - w.shape[1])], 1)
+            x16 = z(16, 69)
+            x16[0:4], x16[4:8], x16[8], x16[9], x16[10:15] = wk[64:68], wv[64:68], wk[68], wv[68], wq[64:69]
+            groups = [w1[:, 0:69], w1[:, 69:138], wq[0:64], wk[0:64], wv[0:64], x16]
+            tc['w_proj_tc'] = torch.cat([umma_bf16x3(p80(gw).contiguous()) for gw in groups]).contiguous()
+            w5p = z(80, 224)   # [h0 (h and h0 blocks folded, 80) | aggr (64) | mu (80)]
+            w5p[:69, 0:69] = (w5[:, 0:69].double() + w5[:, 202:271].double()).float()
+            w5p[:69, 80:144] = w5[:, 69:133]
+            w5p[:69, 144:213] = w5[:, 133:202]
+            tc['w_node_tc'] = torch.cat([umma_bf16x3(w5p), umma_bf16x3(p80(w6).contiguous())]).contiguous()
+            assert tc['w_proj_tc'].numel() * 2 == 161280 and tc['w_node_tc'].numel() * 2 == 138240
+            p80v = lambda v: torch.cat([v, z(80 - v.shape[0])])
+            self.node_consts_host = torch.cat([p80v(b5), p80v(f('node_mlp.3.weight')), p80v(f('node_mlp.3.bias')), b6]).cpu().contiguous()
+            pb = z(320)
+            pb[64:128] = b1
+            self.proj_bias_host = pb.cpu().contiguous()
         self.t = {
             **tc,
             'w_proj': w_proj, 'b_proj': b_proj, 'w_edge1': w_edge1,
@@ -145,6 +168,7 @@ class GraphPlan:
         n_rec = [int(v) for v in n_rec]
         assert len(n_lig) == len(n_rec) and len(n_lig) > 0
         self.n_pairs = len(n_lig)
+        self.forward_ws_bytes = None   # eqd_forward_workspace_bytes(), filled on first use
         self.n_lig_list, self.n_rec_list = n_lig, n_rec
         self.N_l, self.N_r = sum(n_lig), sum(n_rec)
         self.N = self.N_l + self.N_r
@@ -227,18 +251,51 @@ def _pinned_status(n: int) -> torch.Tensor:
     return buf[:n]
 
 
+class NativeStageTimer:
+    """CUDA events recorded by eqd_iegmn_forward around every edge / node stage (io.stage_events), on the launching
+    stream; in the Python driver the same handles are recorded through begin() / end()."""
+
+    def __init__(self):
+        self.lib, self.sets = nat.load(), []
+
+    def new_forward(self, n_layers):
+        arr = (C.c_void_p * (4 * n_layers))(*[self.lib.eqd_event_create() for _ in range(4 * n_layers)])
+        self.sets.append(arr)
+        return arr
+
+    def _pairs(self, name):
+        off = 0 if name == 'edge_stage' else 2
+        for arr in self.sets:
+            for li in range(len(arr) // 4):
+                yield arr[li * 4 + off], arr[li * 4 + off + 1]
+
+    def mean_ms(self, name):
+        v = [self.lib.eqd_event_elapsed_ms(a, b) for a, b in self._pairs(name)]
+        v = [x for x in v if x >= 0]
+        return float(np.mean(v)) if v else None
+
+    def total_ms(self, name):
+        return float(sum(x for x in (self.lib.eqd_event_elapsed_ms(a, b) for a, b in self._pairs(name)) if x >= 0))
+
+    def close(self):
+        for arr in self.sets:
+            for e in arr:
+                self.lib.eqd_event_destroy(e)
+        self.sets = []
+
+
 class IEGMNEngine:
     """Runs the IEGMN stack + keypoints + Kabsch for one plan on the current CUDA stream."""
 
     @staticmethod
     def launches_per_forward(n_layers: int) -> int:
         """Kernels of csrc/ launched by one forward: embed, project (layer 0), per layer edge stage + node stage
-        (layer 0: fp32 node kernel + K/V blocks; 64-wide layers: attention, node MLP, next projections),
-        then head_mean, tile_ptr, head_qbar, head_u, keypoints, keypoint_cov, kabsch_apply."""
+        (attention, node MLP, next layer's projections), then head_mean, tile_ptr, head_qbar, head_u, keypoints,
+        keypoint_cov, kabsch_apply."""
         n = 2 + 7
         for li in range(n_layers):
             last = li == n_layers - 1
-            n += 1 + ((1 + (0 if last else 1)) if li == 0 else (2 + (0 if last else 1)))
+            n += 1 + 2 + (0 if last else 1)
         return n
 
     def __init__(self, device):
@@ -250,6 +307,63 @@ class IEGMNEngine:
     def forward(self, plan: GraphPlan, emb: torch.Tensor, layers: List[PackedLayer], head: PackedHead,
                 res_l, res_r, mu_l, mu_r, x_l, x_r, check_status: bool = True, log=None,
                 stage_timer=None) -> Dict[str, torch.Tensor]:
+        """One forward = ONE call into the library (eqd_iegmn_forward): the per-stage entry points are chained in C on
+        the current stream out of a single workspace allocation.  EQD_PY_FORWARD=1 selects the stage-by-stage Python
+        driver below instead (same kernels; used to A/B the two and by the per-stage tests)."""
+        if _PY_FORWARD:
+            return self._forward_py(plan, emb, layers, head, res_l, res_r, mu_l, mu_r, x_l, x_r, check_status, log,
+                                    stage_timer)
+        lib, dev = self.lib, self.device
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        N, B = plan.N, plan.n_pairs
+        f32 = dict(dtype=torch.float32, device=dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        cf = lambda t: t.to(**f32).contiguous()
+        res_l, res_r, mu_l, mu_r, x_l, x_r = map(cf, (res_l, res_r, mu_l, mu_r, x_l, x_r))
+        assert x_l.shape == (plan.N_l, 3) and x_r.shape == (plan.N_r, 3)
+        g = C.byref(plan.struct)
+        if plan.forward_ws_bytes is None:
+            plan.forward_ws_bytes = int(lib.eqd_forward_workspace_bytes(g))
+        ws = torch.empty(plan.forward_ws_bytes, dtype=torch.uint8, device=dev)
+        # outputs: one fp32 and one fp64 slab, sliced
+        n32 = [B * 9, B * 3, plan.N_l * 3, N * nat.HID]
+        n64 = [B * 3, N * 3, 2 * B * nat.HEADS * 3, B * 9, 2 * B * 3]
+        o32 = torch.empty(sum(n32), **f32).split(n32)
+        o64 = torch.empty(sum(n64), **f64).split(n64)
+        rot, trans, lig_out, h_fin = o32[0].view(B, 3, 3), o32[1].view(B, 1, 3), o32[2].view(plan.N_l, 3), o32[3].view(N, nat.HID)
+        sing, x_fin, keyp, cov, ymean = (o64[0].view(B, 3), o64[1].view(N, 3), o64[2].view(2 * B, nat.HEADS, 3),
+                                         o64[3].view(B, 9), o64[4].view(2 * B, 3))
+        status = torch.empty(B + 1, dtype=torch.int32, device=dev)
+        io = nat.EqdForwardIO()
+        for name, t in (('emb', emb), ('res_lig', res_l), ('res_rec', res_r), ('mu_lig', mu_l), ('mu_rec', mu_r),
+                        ('x_lig', x_l), ('x_rec', x_r), ('rot', rot), ('trans', trans), ('ligand_out', lig_out),
+                        ('sing', sing), ('status', status), ('h_out', h_fin), ('x_out', x_fin), ('keypts', keyp),
+                        ('cov', cov), ('ymean', ymean)):
+            setattr(io, name, t.data_ptr())
+        io.layer0_fp32 = 1 if _LAYER0_FFMA else 0
+        events = stage_timer.new_forward(len(layers)) if stage_timer is not None else None
+        io.stage_events = C.cast(events, C.c_void_p) if events is not None else None
+        larr = (C.POINTER(nat.EqdLayerParams) * len(layers))(*[C.pointer(l.struct) for l in layers])
+        nat.check(lib.eqd_iegmn_forward(g, larr, len(layers), C.byref(head.struct), C.byref(io), nat.ptr(ws),
+                                        plan.forward_ws_bytes, st), 'eqd_iegmn_forward')
+        kab = lambda mask: nat.check(lib.eqd_kabsch_apply(
+            g, nat.ptr(cov), nat.ptr(ymean), nat.ptr(x_l), nat.ptr(mask), nat.ptr(rot), nat.ptr(trans),
+            nat.ptr(lig_out), nat.ptr(sing), nat.ptr(status), st), 'eqd_kabsch_apply')
+        status_host = _pinned_status(B + 2)
+        status_host[:B + 1].copy_(status, non_blocking=True)
+        status_host[B + 1:].copy_(plan.unsorted.to(torch.int32).reshape(1), non_blocking=True)
+        status_event = torch.cuda.Event()
+        status_event.record()
+        out = {'ligand_coors': lig_out, 'keypts': keyp, 'rotation': rot, 'translation': trans, 'h': h_fin,
+               'x64': x_fin, 'cov': cov, 'sing': sing, 'status': status, 'unsorted': plan.unsorted, 'kabsch': kab,
+               'status_host': status_host, 'status_event': status_event, '_keep': (ws, o32, o64, x_l)}
+        if check_status:
+            self.resolve_status(plan, out, kab, log)
+        return out
+
+    def _forward_py(self, plan: GraphPlan, emb: torch.Tensor, layers: List[PackedLayer], head: PackedHead,
+                    res_l, res_r, mu_l, mu_r, x_l, x_r, check_status: bool = True, log=None,
+                    stage_timer=None) -> Dict[str, torch.Tensor]:
         lib, dev = self.lib, self.device
         g = C.byref(plan.struct)
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -274,8 +388,16 @@ class IEGMNEngine:
         kv.view(6, -1)[:, (N // 8) * 1024:].zero_()
         nat.check(lib.eqd_embed(g, nat.ptr(emb), nat.ptr(res_l), nat.ptr(res_r), nat.ptr(mu_l), nat.ptr(mu_r),
                                 nat.ptr(x_l), nat.ptr(x_r), nat.ptr(h0), nat.ptr(x0), st), 'eqd_embed')
-        nat.check(lib.eqd_project(g, C.byref(layers[0].struct), nat.ptr(h0), nat.H0_PAD, nat.ptr(pa), st),
-                  'eqd_project')
+        tc0 = layers[0].dh == nat.H0 and not _LAYER0_FFMA   # 69-wide layer 0 on the tensor cores too
+        if tc0:
+            x5 = torch.empty(((N + 7) // 8 + 8) * 8, 16, **f32)   # channels 64..68 of K, V, Q; pad rows must be finite
+            x5[N:].zero_()
+            mu0 = torch.empty(N, nat.H0_PAD, **f32)
+            nat.check(lib.eqd_project_tc0(g, C.byref(layers[0].struct), nat.ptr(h0), nat.ptr(pa), nat.ptr(kv), nat.ptr(x5),
+                                          st), 'eqd_project_tc0')
+        else:
+            nat.check(lib.eqd_project(g, C.byref(layers[0].struct), nat.ptr(h0), nat.H0_PAD, nat.ptr(pa), st),
+                      'eqd_project')
         h_in, ldh, x_in = h0, nat.H0_PAD, x0
         h_out, x_out = ha, xa
         for li, lay in enumerate(layers):
@@ -294,7 +416,11 @@ class IEGMNEngine:
                 nat.check(lib.eqd_node_stage_tc(g, lp, lpn, nat.ptr(h_in), nat.ptr(h0), nat.ptr(pa), nat.ptr(aggr),
                                                 nat.ptr(kv), nat.ptr(mu), nat.ptr(h_out), nat.ptr(pb), st),
                           f'eqd_node_stage_tc[{li}]')
-            else:                   # 69-wide layer 0: fp32 CUDA-core node stage (fused projections), then K/V blocks
+            elif tc0 and li == 0:   # 69-wide layer 0: 64 tensor-core channels + 5 fp32 ones
+                nat.check(lib.eqd_node_stage_tc0(g, lp, lpn, nat.ptr(h0), nat.ptr(pa), nat.ptr(aggr), nat.ptr(kv),
+                                                 nat.ptr(x5), nat.ptr(mu0), nat.ptr(h_out), nat.ptr(pb), st),
+                          'eqd_node_stage_tc0')
+            else:                   # fp32 CUDA-core node stage (fused projections), then K/V blocks
                 nat.check(lib.eqd_node_stage(g, lp, lpn, nat.ptr(h_in), ldh, nat.ptr(h0), nat.ptr(pa), nat.ptr(aggr),
                                              nat.ptr(h_out), nat.ptr(pb), st), f'eqd_node_stage[{li}]')
                 if nxt is not None:

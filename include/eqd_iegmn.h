@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define EQD_ABI_VERSION 4
+#define EQD_ABI_VERSION 5
 
 #define EQD_EDGE_FEATS 27     /* input_edge_feats_dim, protein_utils.py:71-86 + :373-389 */
 #define EQD_N_RBF 15          /* all_sigmas_dist = 1.5**s, rigid_docking_model.py:116 */
@@ -187,6 +187,13 @@ size_t eqd_kv_blocks_bytes(int32_t n_nodes);
  * bf16x3 blocks into kv and the fp32 columns 192..319 of proj are left untouched (nothing downstream reads them). */
 int eqd_project_tc(const eqd_graph* g, const eqd_layer_params* p, const float* h /*[n][64]*/, float* proj,
                    void* kv, void* stream);
+/* The same for the 69-wide layer 0 (h = h0 [n][72], K padded to 80): proj[n][344] gets Psrc | Pdst | Q[0:64] at
+ * columns 0 / 64 / 128 (the positions the fp32 layer-0 layout uses); K[0:64], V[0:64] go to kv as bf16x3 blocks;
+ * channels 64..68 of K, V, Q go to x5[n][16] = [K64..67 | V64..67 | K68 V68 | Q64..68 | 0] (fp32), which is what
+ * eqd_attention_tc0 adds to the 64-wide tensor-core products.  kv and x5 are required; x5 must have
+ * 8 * (ceil(n / 8) + 8) rows, the rows past n zero (attention reads whole 64-key chunks).                     */
+int eqd_project_tc0(const eqd_graph* g, const eqd_layer_params* p, const float* h0 /*[n][72]*/, float* proj /*[n][344]*/,
+                    void* kv, float* x5 /*[n][16]*/, void* stream);
 /* K/V blocks from the fp32 columns of an existing projection buffer (row stride pw floats). */
 int eqd_kv_blocks(const eqd_graph* g, const float* proj, int32_t pw, int32_t koff, int32_t voff, void* kv,
                   void* stream);
@@ -201,6 +208,25 @@ int eqd_node_mlp_tc(const eqd_graph* g, const eqd_layer_params* p, const float* 
 int eqd_node_stage_tc(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next,
                       const float* h_in, const float* h0, const float* proj, const float* aggr, void* kv,
                       float* mu, float* h_out, float* proj_next, void* stream);
+
+/* ---- the 69-wide layer 0 on the tensor cores.  For p->dh == 69 the tensor-core panel fields of eqd_layer_params hold
+ *   w_proj_tc : 5 groups [64][80] (Psrc, Pdst, Q[0:64], K[0:64], V[0:64]; K = h0 channels 69 -> 80) x 3 splits x 10240 B,
+ *               then one [16][80] group (rows K64..67, V64..67, K68, V68, Q64..68, 0) x 3 splits x 2560 B    (161280 B)
+ *   w_node_tc : node_mlp.0.weight with the h and h0 blocks folded (h = h0 in layer 0), [80][224] = 69 -> 80 outputs over
+ *               K = [h0 80 | aggr 64 | mu 80], 3 splits x 35840 B; node_mlp.4.weight as [64][80] at 107520    (138240 B)
+ *   node_consts_host : HOST [80 + 80 + 80 + 64] = node_mlp.0.bias, node_mlp.3.weight, node_mlp.3.bias (zero padded),
+ *               node_mlp.4.bias;   proj_bias_host : HOST [320], edge_mlp.0.bias at [64, 128).
+ * eqd_attention_tc0: mu[n][72] = softmax(q k^T) v over the partner protein with d = 69: channels 0..63 on the tensor cores
+ * from proj[n][344] (Q at column 128) and kv, channels 64..68 in fp32 from x5; columns 69..71 of mu are written as 0.
+ * eqd_node_mlp_tc0: h_out[n][64] = node_mlp([h0 | aggr | mu | h0]) without skip connection (:332).
+ * eqd_node_stage_tc0 = attention + node MLP + (p_next != NULL) the 64-wide projections of layer 1.              */
+int eqd_attention_tc0(const eqd_graph* g, const float* proj /*[n][344]*/, const void* kv, const float* x5 /*[n+72][16]*/,
+                      float* mu /*[n][72]*/, void* stream);
+int eqd_node_mlp_tc0(const eqd_graph* g, const eqd_layer_params* p, const float* h0 /*[n][72]*/, const float* aggr,
+                     const float* mu /*[n][72]*/, float* h_out /*[n][64]*/, void* stream);
+int eqd_node_stage_tc0(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next, const float* h0,
+                       const float* proj, const float* aggr, void* kv, const float* x5, float* mu, float* h_out,
+                       float* proj_next, void* stream);
 
 /* One whole IEGMN_Layer.forward = eqd_edge_stage + eqd_node_stage (proj must hold this layer's
  * projections on entry; holds the next layer's on exit when p_next != NULL).                  */
@@ -230,6 +256,47 @@ int eqd_keypoints(const eqd_graph* g, const eqd_head_params* hp, const float* h 
 int eqd_kabsch_apply(const eqd_graph* g, const double* cov, const double* ymean, const float* x_lig_in,
                      const int32_t* pair_mask, float* rot, float* trans, float* ligand_out,
                      double* sing, int32_t* status, void* stream);
+
+
+/* ---- the whole hot path in one call ----------------------------------------------------------------------------------
+ * eqd_iegmn_forward = IEGMN.forward (rigid_docking_model.py:452-600: embedding, the n_layers IEGMN layers, keypoint
+ * read-out, Kabsch) + the rigid transform of the ligand (Rigid_Body_Docking_Net.forward :657-665), chained on `stream`
+ * out of the entry points above.  Nothing is allocated: the caller provides eqd_forward_workspace_bytes(g) bytes of
+ * 256-byte aligned device memory.  Layers whose tensor-core panels are present run on the tensor cores, the others on
+ * the fp32 CUDA-core kernels.  All pointers are device memory unless noted.                                          */
+typedef struct eqd_forward_io {
+  /* inputs (reference tensors: residue_emb_layer.weight; ndata['res_feat'], ['mu_r_norm'], ligand ['new_x'], receptor ['x']) */
+  const float* emb;           /* [21][64] */
+  const float* res_lig;       /* [N_l][1] fp32-encoded residue ids */
+  const float* res_rec;
+  const float* mu_lig;        /* [N_l][5] */
+  const float* mu_rec;
+  const float* x_lig;         /* [N_l][3] */
+  const float* x_rec;
+  /* outputs */
+  float* rot;                 /* [B][9]  */
+  float* trans;               /* [B][3]  */
+  float* ligand_out;          /* [N_l][3] transformed ligand coordinates */
+  double* sing;               /* [B][3] singular values */
+  int32_t* status;            /* [B+1] EQD_STATUS_* bits, zeroed by the call */
+  float* h_out;               /* [n][64] last layer's node features  (ndata['hv_iegmn_out']) */
+  double* x_out;              /* [n][3]  last layer's coordinates    (ndata['x_iegmn_out'])  */
+  double* keypts;             /* [2B][50][3] or NULL */
+  double* cov;                /* [B][9] Kabsch covariances (eqd_kabsch_apply can be replayed on them) or NULL */
+  double* ymean;              /* [2B][3] keypoint means (needed for such a replay) or NULL */
+  /* optional: HOST array of 4*n_layers cudaEvent_t handles (edge begin, edge end, node begin, node end per layer) recorded
+   * on `stream`; NULL entries are skipped.  eqd_event_create / _elapsed_ms / _destroy wrap the CUDA calls.          */
+  void* const* stage_events;
+  int32_t layer0_fp32;        /* != 0: keep the 69-wide layer 0 on the fp32 CUDA-core kernels */
+} eqd_forward_io;
+
+size_t eqd_forward_workspace_bytes(const eqd_graph* g);
+int eqd_iegmn_forward(const eqd_graph* g, const eqd_layer_params* const* layers, int32_t n_layers,
+                      const eqd_head_params* hp, const eqd_forward_io* io, void* workspace, size_t workspace_bytes,
+                      void* stream);
+void* eqd_event_create(void);
+void eqd_event_destroy(void* event);
+float eqd_event_elapsed_ms(void* begin, void* end);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ def _header():
 
 
 def test_library_exports_every_declared_symbol():
-    declared = set(re.findall(r'^\s*(?:int|size_t)\s+(eqd_\w+)\s*\(', _header(), flags=re.M))
+    declared = set(re.findall(r'^\s*(?:int|size_t|void\*?|float)\s+(eqd_\w+)\s*\(', _header(), flags=re.M))
     assert declared == set(nat.PROTOTYPES), (declared ^ set(nat.PROTOTYPES))
     lib = nat.load()
     for name in declared:
@@ -48,6 +48,8 @@ def test_struct_layouts_are_natural_c_layouts():
     assert nat.EqdLayerParams.w_node1.offset == 144
     assert ctypes.sizeof(nat.EqdHeadParams) == 5 * 8 + 8
     assert nat.EqdHeadParams.m_qk.offset == 32 and nat.EqdHeadParams.leaky_slope.offset == 40
+    assert ctypes.sizeof(nat.EqdForwardIO) == 18 * 8 + 8 and nat.EqdForwardIO.stage_events.offset == 17 * 8
+    assert nat.EqdForwardIO.layer0_fp32.offset == 18 * 8
 
 
 def test_workspace_bytes_host_arithmetic():
@@ -164,4 +166,4 @@ def test_unsupported_configurations_raise():
 
 
 def test_launch_accounting():
-    assert IEGMNEngine.launches_per_forward(8) == 39 and IEGMNEngine.launches_per_forward(5) == 27
+    assert IEGMNEngine.launches_per_forward(8) == 40 and IEGMNEngine.launches_per_forward(5) == 28
