@@ -58,9 +58,11 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, 0, 14);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, 0, 13);
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int wg_u = warp_u >> 3;
   const bool issuer_warp = (warp_u & 7) == 0;
@@ -177,12 +179,14 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
     float mx = -INFINITY;
     for (int c = 0; c < nchunks; ++c) {
       const int kb_ = c & 1;
+      if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, tile, (c << 4) | 2);
       mbar_wait(&S.k_bar[wg][kb_], kph[kb_]);
       kph[kb_] ^= 1;
       issue_s(kb_, true);
       // the other K buffer was last read by the S GEMM of chunk c-1, already waited for: prefetch into it
       if (c + 1 < nchunks) load_chunk(k_g, G.k[kb_ ^ 1], &S.k_bar[wg][kb_ ^ 1], blk_lo + 8 * (c + 1), kb_ ^ 1);
       else load_chunk(k_g, G.k[kb_ ^ 1], &S.k_bar[wg][kb_ ^ 1], blk_lo, kb_ ^ 1);   // first chunk of pass 2
+      if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, tile, (c << 4) | 3);
       wait_mma();
       float s[32];
       tmem_ld32f(tmem + 96 + half * 32, s);
@@ -208,6 +212,7 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
     float o5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     for (int c = 0; c < nchunks; ++c) {
       const int kb_ = (nchunks + c) & 1, vb_ = c & 1;   // K buffers keep alternating after pass 1
+      if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, tile, (c << 4) | 4);
       mbar_wait(&S.k_bar[wg][kb_], kph[kb_]);
       kph[kb_] ^= 1;
       issue_s(kb_, false);
@@ -215,6 +220,7 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
         load_chunk(k_g, G.k[kb_ ^ 1], &S.k_bar[wg][kb_ ^ 1], blk_lo + 8 * (c + 1), kb_ ^ 1);
         load_chunk(v_g, G.v[vb_ ^ 1], &S.v_bar[wg][vb_ ^ 1], blk_lo + 8 * (c + 1), -1);   // its last reader (P V of c-1) is done
       }
+      if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, tile, (c << 4) | 5);
       wait_mma();
       float s[32];
       tmem_ld32f(tmem + 96 + half * 32, s);
@@ -243,9 +249,11 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
       store_half_split3(tmem + 96 + half * 16, s);
       tc_fence_before();
       wg_barrier(wg);
+      if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, tile, (c << 4) | 6);
       mbar_wait(&S.v_bar[wg][vb_], vph[vb_]);
       vph[vb_] ^= 1;
       issue_pv(vb_, 0u);
+      if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, tile, (c << 4) | 7);
       wait_mma();      // P (= the S region) and this V buffer are free again
       // The tensor core truncates (round-toward-zero) every time it adds into an fp32 accumulator, a systematic
       // bias that grows with the number of accumulation steps; each 64-key chunk is therefore accumulated on its
@@ -256,6 +264,12 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
 #pragma unroll
         for (int i = 0; i < 32; ++i) o_acc[i] += oc[i];
       }
+      // Every thread must have OBSERVED this chunk's v_bar and P.V mma_bar phases before the issuing warp may start the
+      // next ones on the same mbarriers (next chunk's S GEMM commit, the V refill two chunks ahead): a warp that is
+      // held up for a microsecond between the barrier above and its try_wait would otherwise be lapped -- two phase
+      // flips look like none -- and spin forever.  (This was a real, rare hang: ~1 in 10^4 launches back to back.)
+      tc_fence_before();
+      wg_barrier(wg);
     }
     // ---------------- mu = O / l -----------------------------------------------------------------------------
     G.red[r * 2 + half] = l;
@@ -286,10 +300,11 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
     tc_fence_before();
     wg_barrier(wg);
   }
+  if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, 0xffff, 15);
   tc_fence_before();
   __syncthreads();
   TRACE_END(1);
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base), "r"(512));
+  tmem_release(S.tmem_base, warp);
 }
 
 }  // namespace eqd
@@ -299,7 +314,6 @@ EQD_TRACE_SETTER(eqd_trace_set_attn)
 template <bool X5>
 static int launch_attention_tc(const eqd_graph* g, const float* proj, int pw, const void* kv, const float* x5, float* mu,
                                int ldmu, void* stream) {
-  eqd_set_fence_stream(stream);
   if (reinterpret_cast<uintptr_t>(kv) & 15) return EQD_ERR_BAD_ARG;
   if (g->n_node_tiles <= 0) return EQD_OK;
   size_t smem = sizeof(eqd::AtSmem<X5>) + 128;
@@ -314,14 +328,12 @@ static int launch_attention_tc(const eqd_graph* g, const float* proj, int pw, co
 }
 
 extern "C" int eqd_attention_tc(const eqd_graph* g, const float* proj, const void* kv, float* mu, void* stream) {
-  eqd_set_fence_stream(stream);
   if (!g || !proj || !kv || !mu) return EQD_ERR_BAD_ARG;
   return launch_attention_tc<false>(g, proj, 320, kv, nullptr, mu, EQD_HID, stream);
 }
 
 extern "C" int eqd_attention_tc0(const eqd_graph* g, const float* proj, const void* kv, const float* x5, float* mu,
                                  void* stream) {
-  eqd_set_fence_stream(stream);
   if (!g || !proj || !kv || !x5 || !mu) return EQD_ERR_BAD_ARG;
   if (reinterpret_cast<uintptr_t>(x5) & 15) return EQD_ERR_BAD_ARG;
   return launch_attention_tc<true>(g, proj, 128 + 3 * 72, kv, x5, mu, EQD_H0_PAD, stream);

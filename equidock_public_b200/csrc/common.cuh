@@ -18,22 +18,11 @@
 #define EQD_THREADS 128
 #define EQD_TM 128
 
-// After every launch: (1) launch-error check, (2) a stream fence (see eqd_launch_fence in head.cu).
 #define EQD_CUDA_LAUNCH_CHECK()                          \
   do {                                                   \
     cudaError_t e__ = cudaGetLastError();                \
     if (e__ != cudaSuccess) return -(1000 + (int)e__);   \
-    eqd_launch_fence();                                  \
   } while (0)
-
-// Records a (timing-disabled) event on the stream of the launch that just happened.  Without any stream operation
-// between back-to-back tensor-core kernels a long run of forwards (hundreds) eventually leaves one CTA spinning on an
-// mbarrier -- reproduced with scripts/forward_stress.py, never with an event (or any other stream marker) between the
-// kernels, under cuda-gdb, or with CUDA_LAUNCH_BLOCKING=1; each kernel alone survives tens of thousands of launches
-// (scripts/kernel_stress.py).  The root cause is not understood yet (DESIGN.md "known issues"); the fence costs about
-// a microsecond per launch.  EQD_LAUNCH_FENCE=0 disables it.
-extern "C" void eqd_set_fence_stream(void* stream);
-void eqd_launch_fence();
 
 namespace eqd {
 

@@ -420,7 +420,7 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
   tc_fence_before();
   __syncthreads();
   TRACE_END(0);
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base), "r"(512));
+  tmem_release(S.tmem_base, warp);
 }
 
 }  // namespace eqd
@@ -429,7 +429,6 @@ EQD_TRACE_SETTER(eqd_trace_set_edge)
 
 extern "C" int eqd_edge_stage(const eqd_graph* g, const eqd_layer_params* p, const float* proj, const double* x_in,
                               const double* x_orig, float* aggr, double* x_out, int32_t* status, void* stream) {
-  eqd_set_fence_stream(stream);
   if (!g || !p || !proj || !x_in || !x_orig || !aggr || !x_out || !status) return EQD_ERR_BAD_ARG;
   if (!p->w_edge_tc || !p->edge_consts_host) return EQD_ERR_BAD_ARG;
   if (g->max_in_degree < 1 || g->max_in_degree > EQD_TM) return EQD_ERR_UNSUPPORTED;

@@ -68,7 +68,6 @@ EQD_TRACE_SETTER(eqd_trace_set_embed)
 extern "C" int eqd_embed(const eqd_graph* g, const float* emb, const float* res_feat_lig, const float* res_feat_rec,
                          const float* mu_lig, const float* mu_rec, const float* x_lig, const float* x_rec, float* h0,
                          double* x64, void* stream) {
-  eqd_set_fence_stream(stream);
   if (!g || !emb || !h0 || !x64) return EQD_ERR_BAD_ARG;
   if (g->n_nodes <= 0) return EQD_OK;
   long total = (long)g->n_nodes * (EQD_H0_PAD / 4);
@@ -82,7 +81,6 @@ extern "C" int eqd_embed(const eqd_graph* g, const float* emb, const float* res_
 
 extern "C" int eqd_project(const eqd_graph* g, const eqd_layer_params* p, const float* h, int32_t ldh, float* proj,
                            void* stream) {
-  eqd_set_fence_stream(stream);
   if (!g || !p || !h || !proj) return EQD_ERR_BAD_ARG;
   if (!((p->dh == 64 && p->dhp == 64) || (p->dh == 69 && p->dhp == 72))) return EQD_ERR_UNSUPPORTED;
   if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)

@@ -3,6 +3,7 @@
 // per-stage entry points of this library on one stream, so a binding pays one foreign call (and ~40 kernel launches)
 // per batch instead of ~45 calls plus as many device allocations.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -62,6 +63,8 @@ extern "C" int eqd_iegmn_forward(const eqd_graph* g, const eqd_layer_params* con
   if (reinterpret_cast<uintptr_t>(workspace) & 255) return EQD_ERR_BAD_ARG;
   if (g->n_pairs <= 0 || g->n_nodes <= 0) return EQD_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  // debugging knobs (bit mask): 1 skip the head, 2 skip the memsets, 4 synchronise after every stage, 8 stop after layer 0
+  static const int dbg = getenv("EQD_FORWARD_DEBUG") ? atoi(getenv("EQD_FORWARD_DEBUG")) : 0;
   unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
   float* h0 = reinterpret_cast<float*>(w + c.h0);
   double* x0 = reinterpret_cast<double*>(w + c.x0);
@@ -80,7 +83,7 @@ extern "C" int eqd_iegmn_forward(const eqd_graph* g, const eqd_layer_params* con
 
   // rows the kernels never write but the tensor cores / TMA read: the tail of the last 8-node block and the 8 pad
   // blocks of each (K|V, split) plane, and the pad rows of x5 (they reach P.V as 0 x value: must be finite)
-  {
+  if (!(dbg & 2)) {
     const size_t plane = c.kv_bytes / 6, from = (size_t)(N / 8) * 1024;
     for (int pl = 0; pl < 6; ++pl) cudaMemsetAsync(kv + pl * plane + from, 0, plane - from, st);
     cudaMemsetAsync(x5 + (size_t)N * 16, 0, (c.x5_rows - (size_t)N) * 16 * 4, st);
@@ -120,11 +123,14 @@ extern "C" int eqd_iegmn_forward(const eqd_graph* g, const eqd_layer_params* con
     }
     if (rc) return rc;
     stage_event(li, 3);
+    if (dbg & 4) cudaStreamSynchronize(st);
+    if ((dbg & 8) && li == 0) return EQD_OK;
     float* t = pa; pa = pb; pb = t;
     h_in = h_out;
     ldh = EQD_HID;
     x_in = x_out;
   }
+  if (dbg & 1) return EQD_OK;
   rc = eqd_keypoints(g, hp, h_in, x_in, w + c.head, c.head_bytes, keypts, ymean, cov, stream);
   if (rc) return rc;
   return eqd_kabsch_apply(g, cov, ymean, io->x_lig, nullptr, io->rot, io->trans, io->ligand_out, io->sing, io->status, stream);

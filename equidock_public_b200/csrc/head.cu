@@ -444,23 +444,6 @@ static inline size_t eqd_align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 extern "C" int eqd_abi_version(void) { return EQD_ABI_VERSION; }
 
-// ---- launch fence (see common.cuh) ---------------------------------------------------------------------------------
-static thread_local cudaStream_t g_fence_stream = nullptr;
-extern "C" void eqd_set_fence_stream(void* stream) { g_fence_stream = (cudaStream_t)stream; }
-void eqd_launch_fence() {
-  static const bool enabled = !(getenv("EQD_LAUNCH_FENCE") && atoi(getenv("EQD_LAUNCH_FENCE")) == 0);
-  if (!enabled) return;
-  static thread_local cudaEvent_t ev = nullptr;
-  static thread_local int ev_device = -1;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (ev == nullptr || ev_device != dev) {
-    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; return; }
-    ev_device = dev;
-  }
-  cudaEventRecord(ev, g_fence_stream);
-}
-
 static inline size_t ws_part_bytes(int32_t n_node_tiles) { return eqd_align256((size_t)(n_node_tiles > 0 ? n_node_tiles : 1) * 64 * sizeof(float)); }
 static inline size_t ws_tile_ptr_bytes(int32_t n_pairs) { return eqd_align256((size_t)(2 * (n_pairs > 0 ? n_pairs : 0) + 1) * sizeof(int)); }
 static inline size_t ws_qbar_bytes(int32_t n_pairs) { return eqd_align256((size_t)2 * (n_pairs > 0 ? n_pairs : 1) * 64 * sizeof(double)); }
@@ -473,7 +456,6 @@ extern "C" size_t eqd_workspace_bytes(int32_t n_nodes, int32_t n_node_tiles, int
 }
 
 extern "C" int eqd_head_fold(const eqd_head_params* hp, double* m_qk, void* stream) {
-  eqd_set_fence_stream(stream);
   if (!hp || !hp->w_key || !hp->w_query || !m_qk) return EQD_ERR_BAD_ARG;
   eqd::head_fold_kernel<<<EQD_HEADS, 256, 0, (cudaStream_t)stream>>>(*hp, m_qk);
   EQD_CUDA_LAUNCH_CHECK();
@@ -483,7 +465,6 @@ extern "C" int eqd_head_fold(const eqd_head_params* hp, double* m_qk, void* stre
 extern "C" int eqd_keypoints(const eqd_graph* g, const eqd_head_params* hp, const float* h, const double* x,
                              void* workspace, size_t workspace_bytes, double* keypts, double* ymean, double* cov,
                              void* stream) {
-  eqd_set_fence_stream(stream);
   if (!g || !hp || !h || !x || !workspace || !keypts || !ymean || !cov) return EQD_ERR_BAD_ARG;
   if (!hp->m_qk || (reinterpret_cast<uintptr_t>(hp->m_qk) & 15)) return EQD_ERR_BAD_ARG;   // eqd_head_fold() output
   if (workspace_bytes < eqd_workspace_bytes(g->n_nodes, g->n_node_tiles, g->n_pairs)) return EQD_ERR_WORKSPACE;
@@ -531,7 +512,6 @@ extern "C" int eqd_keypoints(const eqd_graph* g, const eqd_head_params* hp, cons
 extern "C" int eqd_kabsch_apply(const eqd_graph* g, const double* cov, const double* ymean, const float* x_lig_in,
                                 const int32_t* pair_mask, float* rot, float* trans, float* ligand_out, double* sing,
                                 int32_t* status, void* stream) {
-  eqd_set_fence_stream(stream);
   if (!g || !cov || !ymean || !x_lig_in || !rot || !trans || !ligand_out || !sing || !status) return EQD_ERR_BAD_ARG;
   if (g->n_pairs <= 0) return EQD_OK;
   eqd::kabsch_apply_kernel<<<g->n_pairs, 128, 0, (cudaStream_t)stream>>>(*g, cov, ymean, x_lig_in, pair_mask, rot,

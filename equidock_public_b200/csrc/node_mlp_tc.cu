@@ -235,7 +235,7 @@ node_mlp_tc_kernel(int n_nodes, eqd_layer_params p, const __grid_constant__ NmCo
   tc_fence_before();
   __syncthreads();
   TRACE_END(3);
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base), "r"(512));
+  tmem_release(S.tmem_base, warp);
 }
 
 
@@ -475,7 +475,7 @@ node_mlp0_tc_kernel(int n_nodes, eqd_layer_params p, const __grid_constant__ Nm0
   tc_fence_before();
   __syncthreads();
   TRACE_END(3);
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base), "r"(512));
+  tmem_release(S.tmem_base, warp);
 }
 
 }  // namespace eqd
@@ -484,7 +484,6 @@ EQD_TRACE_SETTER(eqd_trace_set_mlp)
 
 extern "C" int eqd_node_mlp_tc(const eqd_graph* g, const eqd_layer_params* p, const float* h_in, const float* aggr,
                                const float* mu, const float* h0, float* h_out, void* stream) {
-  eqd_set_fence_stream(stream);
   if (!g || !p || !h_in || !aggr || !mu || !h0 || !h_out) return EQD_ERR_BAD_ARG;
   if (p->dh != 64 || p->dhp != 64) return EQD_ERR_UNSUPPORTED;
   if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)
@@ -504,7 +503,6 @@ extern "C" int eqd_node_mlp_tc(const eqd_graph* g, const eqd_layer_params* p, co
 
 extern "C" int eqd_node_mlp_tc0(const eqd_graph* g, const eqd_layer_params* p, const float* h0, const float* aggr,
                                 const float* mu, float* h_out, void* stream) {
-  eqd_set_fence_stream(stream);
   if (!g || !p || !h0 || !aggr || !mu || !h_out) return EQD_ERR_BAD_ARG;
   if (p->dh != 69 || p->dhp != 72) return EQD_ERR_UNSUPPORTED;
   if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)
@@ -528,7 +526,6 @@ extern "C" int eqd_attention_tc0(const eqd_graph*, const float*, const void*, co
 extern "C" int eqd_node_stage_tc0(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next,
                                   const float* h0, const float* proj, const float* aggr, void* kv, const float* x5,
                                   float* mu, float* h_out, float* proj_next, void* stream) {
-  eqd_set_fence_stream(stream);
   if (!g || !p || !kv || !mu || !x5) return EQD_ERR_BAD_ARG;
   if (p_next && !proj_next) return EQD_ERR_BAD_ARG;
   int rc = eqd_attention_tc0(g, proj, kv, x5, mu, stream);
@@ -545,7 +542,6 @@ extern "C" int eqd_attention_tc(const eqd_graph*, const float*, const void*, flo
 extern "C" int eqd_node_stage_tc(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next,
                                  const float* h_in, const float* h0, const float* proj, const float* aggr, void* kv,
                                  float* mu, float* h_out, float* proj_next, void* stream) {
-  eqd_set_fence_stream(stream);
   if (!g || !p || !kv || !mu) return EQD_ERR_BAD_ARG;
   if (p_next && !proj_next) return EQD_ERR_BAD_ARG;
   int rc = eqd_attention_tc(g, proj, kv, mu, stream);

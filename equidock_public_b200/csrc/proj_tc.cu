@@ -224,7 +224,7 @@ project_tc_kernel(int n_nodes, eqd_layer_params p, const __grid_constant__ PjCon
   tc_fence_before();
   __syncthreads();
   TRACE_END(2);
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base), "r"(512));
+  tmem_release(S.tmem_base, warp);
 }
 
 // fp32 K / V columns of a projection buffer -> bf16x3 8-node blocks (used after the FFMA layer-0 node stage)
@@ -255,7 +255,6 @@ extern "C" size_t eqd_kv_blocks_bytes(int32_t n_nodes) {
 template <bool L0>
 static int launch_project_tc(const eqd_graph* g, const eqd_layer_params* p, const float* h, int ldh, float* proj, int pw,
                              void* kv, float* x5, void* stream) {
-  eqd_set_fence_stream(stream);
   if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)
   if (!p->w_proj_tc || !p->proj_bias_host || (reinterpret_cast<uintptr_t>(p->w_proj_tc) & 15)) return EQD_ERR_BAD_ARG;
   if (g->n_nodes <= 0) return EQD_OK;
@@ -276,7 +275,6 @@ static int launch_project_tc(const eqd_graph* g, const eqd_layer_params* p, cons
 
 extern "C" int eqd_project_tc(const eqd_graph* g, const eqd_layer_params* p, const float* h, float* proj, void* kv,
                               void* stream) {
-  eqd_set_fence_stream(stream);
   if (!g || !p || !h || !proj) return EQD_ERR_BAD_ARG;
   if (p->dh != 64 || p->dhp != 64) return EQD_ERR_UNSUPPORTED;
   return launch_project_tc<false>(g, p, h, EQD_HID, proj, 320, kv, nullptr, stream);
@@ -284,7 +282,6 @@ extern "C" int eqd_project_tc(const eqd_graph* g, const eqd_layer_params* p, con
 
 extern "C" int eqd_project_tc0(const eqd_graph* g, const eqd_layer_params* p, const float* h0, float* proj, void* kv,
                                float* x5, void* stream) {
-  eqd_set_fence_stream(stream);
   if (!g || !p || !h0 || !proj || !kv || !x5) return EQD_ERR_BAD_ARG;
   if (p->dh != 69 || p->dhp != 72) return EQD_ERR_UNSUPPORTED;
   return launch_project_tc<true>(g, p, h0, EQD_H0_PAD, proj, 128 + 3 * 72, kv, x5, stream);
@@ -292,7 +289,6 @@ extern "C" int eqd_project_tc0(const eqd_graph* g, const eqd_layer_params* p, co
 
 extern "C" int eqd_kv_blocks(const eqd_graph* g, const float* proj, int32_t pw, int32_t koff, int32_t voff, void* kv,
                              void* stream) {
-  eqd_set_fence_stream(stream);
   if (!g || !proj || !kv) return EQD_ERR_BAD_ARG;
   if (g->n_nodes <= 0) return EQD_OK;
   long split_stride = (long)((g->n_nodes + 7) / 8 + 8) * 1024;

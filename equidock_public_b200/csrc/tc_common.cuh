@@ -113,6 +113,11 @@ __device__ __forceinline__ void issue_gemm_n(unsigned d_tmem, unsigned a_base, u
       accum = 1;
     }
 }
+// End of a kernel that owns tensor memory: every thread has passed its last tcgen05 operation (callers fence + sync
+// first); warp 0, which allocated the 512 columns, releases them.
+__device__ __forceinline__ void tmem_release(unsigned tmem_base, int warp) {
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
 __device__ __forceinline__ bool elect_one() {
   unsigned pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));

@@ -39,7 +39,7 @@ def umma_bf16x3(w: torch.Tensor) -> torch.Tensor:
 # EQD_LAYER0_FFMA=1 keeps the 69-wide layer 0 on the fp32 CUDA-core kernels (A/B comparisons)
 _LAYER0_FFMA = bool(int(__import__('os').environ.get('EQD_LAYER0_FFMA', '0')))
 # EQD_PY_FORWARD=1: drive the stages one C call at a time from Python instead of through eqd_iegmn_forward
-_PY_FORWARD = bool(int(__import__('os').environ.get('EQD_PY_FORWARD', '1')))
+_PY_FORWARD = bool(int(__import__('os').environ.get('EQD_PY_FORWARD', '0')))
 
 
 class PackedLayer:
@@ -325,14 +325,11 @@ class IEGMNEngine:
         if plan.forward_ws_bytes is None:
             plan.forward_ws_bytes = int(lib.eqd_forward_workspace_bytes(g))
         ws = torch.empty(plan.forward_ws_bytes, dtype=torch.uint8, device=dev)
-        # outputs: one fp32 and one fp64 slab, sliced
-        n32 = [B * 9, B * 3, plan.N_l * 3, N * nat.HID]
-        n64 = [B * 3, N * 3, 2 * B * nat.HEADS * 3, B * 9, 2 * B * 3]
-        o32 = torch.empty(sum(n32), **f32).split(n32)
-        o64 = torch.empty(sum(n64), **f64).split(n64)
-        rot, trans, lig_out, h_fin = o32[0].view(B, 3, 3), o32[1].view(B, 1, 3), o32[2].view(plan.N_l, 3), o32[3].view(N, nat.HID)
-        sing, x_fin, keyp, cov, ymean = (o64[0].view(B, 3), o64[1].view(N, 3), o64[2].view(2 * B, nat.HEADS, 3),
-                                         o64[3].view(B, 9), o64[4].view(2 * B, 3))
+        # outputs (separate allocations: the kernels assume 16-byte aligned rows)
+        rot, trans = torch.empty(B, 3, 3, **f32), torch.empty(B, 1, 3, **f32)
+        lig_out, h_fin = torch.empty(plan.N_l, 3, **f32), torch.empty(N, nat.HID, **f32)
+        sing, x_fin = torch.empty(B, 3, **f64), torch.empty(N, 3, **f64)
+        keyp, cov, ymean = torch.empty(2 * B, nat.HEADS, 3, **f64), torch.empty(B, 9, **f64), torch.empty(2 * B, 3, **f64)
         status = torch.empty(B + 1, dtype=torch.int32, device=dev)
         io = nat.EqdForwardIO()
         for name, t in (('emb', emb), ('res_lig', res_l), ('res_rec', res_r), ('mu_lig', mu_l), ('mu_rec', mu_r),
@@ -356,7 +353,7 @@ class IEGMNEngine:
         status_event.record()
         out = {'ligand_coors': lig_out, 'keypts': keyp, 'rotation': rot, 'translation': trans, 'h': h_fin,
                'x64': x_fin, 'cov': cov, 'sing': sing, 'status': status, 'unsorted': plan.unsorted, 'kabsch': kab,
-               'status_host': status_host, 'status_event': status_event, '_keep': (ws, o32, o64, x_l)}
+               'status_host': status_host, 'status_event': status_event, '_keep': (ws, ymean, x_l)}
         if check_status:
             self.resolve_status(plan, out, kab, log)
         return out
