@@ -142,8 +142,8 @@ def edge_stage_algorithmic_flops(n_edges: int, dh: int = 64) -> float:
 # bf16 FLOPs the tensor-core edge stage really issues per edge: (K 48 x N 64 + K 64 x N 128) MACs x 6 split products
 EDGE_TC_BF16_FLOP_PER_EDGE = 2.0 * (48 * 64 + 64 * 128) * 6
 # dram__bytes_read.sum + dram__bytes_write.sum of one edge_stage_tc_kernel launch of this workload (ncu --set full,
-# profiles/r01_v2_edge_stage_tc_ncu_summary.txt): 176.5 MB + 19.3 MB
-EDGE_TC_NCU_TRAFFIC_BYTES = 195.8e6
+# profiles/r01_v3_edge_stage_tc_ncu_summary.txt): 176.5 MB + 18.0 MB
+EDGE_TC_NCU_TRAFFIC_BYTES = 194.5e6
 
 
 def effective_cores() -> int:

@@ -309,3 +309,53 @@ def test_c_abi_rejects_bad_arguments(cuda_device):
                               nat.ptr(one), nat.ptr(one), None) == -1          # tensor-core panels missing
     assert lib.eqd_node_mlp_tc(C.byref(g), C.byref(lp), nat.ptr(one), nat.ptr(one), nat.ptr(one), nat.ptr(one),
                                nat.ptr(one), None) == -2                         # 48-wide layer
+
+
+def test_one_call_forward_equals_stage_by_stage_driver(models, cuda_device, monkeypatch):
+    """eqd_iegmn_forward (one C call, one workspace) chains exactly the kernels the Python driver launches one by
+    one: outputs are bitwise identical, for both checkpoints (5 shared layers / 8 layers) and a ragged batch."""
+    from equidock_public_b200 import engine as eng
+    for ds in ('db5', 'dips'):
+        names, pairs, _, _ = gio.load_pairs(ds)
+        outs = {}
+        for py in (False, True):
+            monkeypatch.setattr(eng, '_PY_FORWARD', py)
+            g = gio.make_batch([pairs[n] for n in names[:3]], cuda_device)
+            coors, kl, kr, rot, tr = models[ds](g, epoch=0)
+            outs[py] = (torch.cat(coors), torch.stack(rot), torch.stack(tr), torch.stack(kl), torch.stack(kr),
+                        g.nodes['ligand'].data['hv_iegmn_out'].clone(), g.nodes['receptor'].data['x_iegmn_out'].clone())
+        for a, b in zip(outs[False], outs[True]):
+            assert torch.equal(a, b)
+
+
+def test_layer0_tensor_core_path_vs_fp32_cuda_core_path(models, cuda_device, monkeypatch):
+    """The 69-wide layer 0 on the tensor cores (K = 80 panels, 64 TC + 5 fp32 attention channels) against the fp32
+    CUDA-core kernels for the same layer: the two evaluate the same formulas with different roundings."""
+    from equidock_public_b200 import engine as eng
+    names, pairs, outs, _ = gio.load_pairs('dips')
+    res = {}
+    for ffma in (False, True):
+        monkeypatch.setattr(eng, '_LAYER0_FFMA', ffma)
+        g = gio.make_batch([pairs[n] for n in names], cuda_device)
+        coors, _, _, rot, _ = models['dips'](g, epoch=0)
+        res[ffma] = (coors, rot)
+    for i, n in enumerate(names):
+        yard = np.abs(outs[n]['ref32']['ligand_coors'] - outs[n]['ref64']['ligand_coors']).max()
+        d = (res[False][0][i] - res[True][0][i]).abs().max().item()
+        assert d <= 2 * max(COORD_TOL, 2 * yard), (n, d, yard)
+
+
+@pytest.mark.timeout(180)
+def test_many_back_to_back_forwards_do_not_deadlock(models, cuda_device):
+    """Regression for a rare attention-kernel deadlock (a warp lapped on an mbarrier): a few hundred forwards queued
+    back to back on a multi-tile batch; the run is bounded by pytest-timeout rather than by an assertion."""
+    pairs = synthetic.synthetic_batch(64, 200, 200, 10, seed=3)
+    g = gio.make_batch(pairs, cuda_device)
+    pend = None
+    for _ in range(300):
+        nxt = models['dips'].forward_async(g, 0)
+        if pend is not None:
+            pend.result()
+        pend = nxt
+    out = pend.result()
+    assert torch.isfinite(torch.cat(out[0])).all()
