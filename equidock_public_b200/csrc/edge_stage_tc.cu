@@ -14,8 +14,6 @@
 //   GEMM2+3 (24 mma, N=128: [W2 ; W3 W2] on the same A) -> msg (+bias) -> fp32 tile in smem (mean aggregation)
 //     and the coordinate MLP's hidden layer -> LeakyReLU, dot w4 -> phi ; x' = eta x0 + (1-eta) x + mean(x_rel phi) in fp64.
 // Per-edge activations never leave the SM; weights are read from HBM/L2 once per CTA.
-#include <cstdlib>
-
 #include "tc_common.cuh"
 
 namespace eqd {
@@ -57,7 +55,7 @@ struct EdgeConsts {                       // per-layer vectors, passed by value 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ EdgeConsts cst,
                      const float* __restrict__ proj, const double* __restrict__ x_in, const double* __restrict__ x_orig,
-                     float* __restrict__ aggr, double* __restrict__ x_out, int* __restrict__ status, int tn, unsigned stagger_ns) {
+                     float* __restrict__ aggr, double* __restrict__ x_out, int* __restrict__ status, int tn) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
   const int tid = threadIdx.x, wg = tid >> 8, q = tid & 255, half = q >> 7, r = q & 127, warp = tid >> 5;
@@ -163,9 +161,6 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     cp_async_commit();
   };
 
-  // The two tile groups run identical code: started together they stay in phase and collide on the tensor pipe, the
-  // LSU and the barriers instead of filling each other's waits.  Hold group 1 back by about half a tile.
-  if (wg == 1 && stagger_ns > 0) __nanosleep(stagger_ns);
   int tile = blockIdx.x * 2 + wg;
   const int tstride = gridDim.x * 2;
   const int lane = tid & 31, wrow0 = 32 * (warp & 3);
@@ -446,9 +441,8 @@ extern "C" int eqd_edge_stage(const eqd_graph* g, const eqd_layer_params* p, con
   cudaFuncSetAttribute(eqd::edge_stage_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int grid = (ntiles + 1) / 2;
   if (grid > 148) grid = 148;
-  static const unsigned stagger_ns = getenv("EQD_EDGE_STAGGER_NS") ? (unsigned)atoi(getenv("EQD_EDGE_STAGGER_NS")) : 0u;
   eqd::edge_stage_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(*g, *p, cst, proj, x_in, x_orig, aggr, x_out,
-                                                                             status, tn, stagger_ns);
+                                                                             status, tn);
   EQD_CUDA_LAUNCH_CHECK();
   return EQD_OK;
 }
