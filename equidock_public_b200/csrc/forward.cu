@@ -53,9 +53,11 @@ extern "C" int eqd_iegmn_forward(const eqd_graph* g, const eqd_layer_params* con
                                  const eqd_head_params* hp, const eqd_forward_io* io, void* workspace,
                                  size_t workspace_bytes, void* stream) {
   if (!g || !layers || n_layers < 1 || !hp || !io || !workspace) return EQD_ERR_BAD_ARG;
-  if (!io->emb || !io->x_lig || !io->x_rec || !io->rot || !io->trans || !io->ligand_out || !io->sing || !io->status ||
-      !io->h_out || !io->x_out)
+  if (!io->emb || !io->res_lig || !io->res_rec || !io->mu_lig || !io->mu_rec || !io->x_lig || !io->x_rec || !io->rot ||
+      !io->trans || !io->ligand_out || !io->sing || !io->status || !io->h_out || !io->x_out)
     return EQD_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(io->h_out) | reinterpret_cast<uintptr_t>(io->x_out)) & 15)
+    return EQD_ERR_BAD_ARG;   // rows are written 16 bytes at a time
   for (int li = 0; li < n_layers; ++li)
     if (!layers[li]) return EQD_ERR_BAD_ARG;
   const Carve c = carve(g);

@@ -52,6 +52,37 @@ def test_struct_layouts_are_natural_c_layouts():
     assert nat.EqdForwardIO.layer0_fp32.offset == 18 * 8
 
 
+def _header_struct_fields(name):
+    """Field names of `typedef struct <name> { ... } <name>;` in declaration order (comments stripped)."""
+    body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (name, name), _header(), flags=re.S).group(1)
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    fields = []
+    for decl in body.split(';'):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(','):
+            fields.append(re.findall(r'(\w+)\s*$', part.strip())[0])
+    return fields
+
+
+@pytest.mark.parametrize('cname,ctype', [('eqd_graph', nat.EqdGraph), ('eqd_layer_params', nat.EqdLayerParams),
+                                         ('eqd_head_params', nat.EqdHeadParams), ('eqd_forward_io', nat.EqdForwardIO)])
+def test_ctypes_structs_list_the_header_fields_in_order(cname, ctype):
+    assert _header_struct_fields(cname) == [f[0] for f in ctype._fields_]
+
+
+def test_forward_workspace_bytes_host_arithmetic():
+    lib = nat.load()
+    g = nat.EqdGraph()
+    g.n_pairs, g.n_nodes, g.n_node_tiles = 256, 102400, 1024
+    need = lib.eqd_forward_workspace_bytes(ctypes.byref(g))
+    # two projection buffers (344 floats per node) dominate; everything is 256-byte aligned
+    assert need > 2 * 102400 * 344 * 4 and need % 256 == 0
+    assert need >= lib.eqd_kv_blocks_bytes(102400) + lib.eqd_workspace_bytes(102400, 1024, 256)
+    assert lib.eqd_forward_workspace_bytes(None) == 0
+
+
 def test_workspace_bytes_host_arithmetic():
     lib = nat.load()
     assert lib.eqd_workspace_bytes(1000, 10, 3) >= 10 * 64 * 4 + 7 * 4
