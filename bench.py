@@ -386,7 +386,12 @@ def main():
     ap.add_argument('--ref-sample', type=int, default=128, help='pairs per step of the CPU reference arm')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--watchdog-seconds', type=int, default=1500,
+                    help='abort (with a stack dump) instead of stalling forever if the run has not finished by then')
     args = ap.parse_args()
+    if args.watchdog_seconds > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog_seconds, exit=True)
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
