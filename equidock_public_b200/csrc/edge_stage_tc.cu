@@ -3,16 +3,17 @@
 // a*w ~ a0w0 + a0w1 + a1w0 + a0w2 + a1w1 + a2w0, fp32 accumulation in TMEM; measured error below a
 // plain fp32 FMA loop, see scripts/tc_probe.cu).
 //
-// One persistent CTA per SM, 2 warpgroups; each warpgroup owns one tile of <=128 edges at a time
-// (thread r <-> edge row r <-> TMEM lane r), the two run out of phase so one's MMA phase overlaps the
-// other's epilogue.  Per tile and warpgroup:
+// One persistent CTA per SM, 2 tile groups of 256 threads; each group owns one tile of <=128 edges at a time
+// (2 threads per edge row: thread (r, half) <-> columns [32 half, +32) of row r <-> TMEM lane r), the two groups run
+// out of phase so one's MMA phases overlap the other's epilogues.  Per tile and group:
 //   he rows (cp.async.bulk -> smem staging, prefetched one tile ahead) + 15 RBFs
 //     -> [he|rbf] bf16x3 -> TMEM (tcgen05.st)                      A operand of GEMM1 (K=48)
 //   GEMM1 (18 tcgen05.mma, B = edge_mlp.0.weight[:, 2dh:] bf16x3 resident in smem)
-//     -> + gathered Psrc[src] + Pdst[dst] (cp.async into smem), LeakyReLU, LayerNorm (one row per
-//        thread: no shuffles) -> bf16x3 -> TMEM
-//   GEMM2+3 (24 mma, N=128: [W2 ; W3 W2] on the same A) -> msg (+bias) -> fp32 tile in smem (mean aggregation)
-//     and the coordinate MLP's hidden layer -> LeakyReLU, dot w4 -> phi ; x' = eta x0 + (1-eta) x + mean(x_rel phi) in fp64.
+//     -> + gathered Psrc[src] + Pdst[dst] (cp.async into smem), LeakyReLU, LayerNorm (the two halves of a row
+//        combine their statistics through smem) -> bf16x3 -> TMEM
+//   GEMM2 and GEMM3 on that one A operand (2 x 24 mma, N=64 halves of the stacked panel [W2 ; W3 W2])
+//     -> msg (+bias) -> fp32 tile in smem (mean aggregation at the destination nodes)
+//     -> coordinate MLP hidden layer -> LeakyReLU, dot w4 -> phi ; x' = eta x0 + (1-eta) x + mean(x_rel phi) in fp64.
 // Per-edge activations never leave the SM; weights are read from HBM/L2 once per CTA.
 #include "tc_common.cuh"
 

@@ -4,8 +4,9 @@
 // reach O(10^3) A, so this is where fp32 rounding would cost 1e-4 A.
 //
 // Algebra: the reference materialises keys (n x 3200) and compares them with the 3200-d query;
-//   logits[k][j] = <W_K,k h_j , W_Q,k qbar> / sqrt(64) = h_j . u_k,   u_k = W_K,k^T (W_Q,k qbar) / 8
-// so only u (50 x 64) is formed -- 20x fewer FLOPs, same value up to rounding.
+//   logits[k][j] = <W_K,k h_j , W_Q,k qbar> / sqrt(64) = h_j . u_k,   u_k = (W_K,k^T W_Q,k / 8) qbar = m_qk[k]^T qbar
+// so only u (50 x 64) is formed per protein, from 50 64x64 matrices folded once per model (eqd_head_fold; SURVEY 8a
+// row a9) -- 40x fewer FLOPs, same value up to rounding.
 #include <cstdlib>
 
 #include "common.cuh"

@@ -1,9 +1,10 @@
-// Node projections of a 64-wide layer on the tensor cores (tcgen05, bf16x6):
-//   proj[n] = [Psrc | Pdst | Q | K | V] = act(h[n] . Wp + b)      (5 groups of 64 columns, see eqd_layer_params)
+// Node projections of a layer on the tensor cores (tcgen05, bf16x6; att_mlp_Q/K/V :130-140 and the [h_src|h_dst]
+// columns of edge_mlp.0 :120, applied per node):
+//   proj[n] = [Psrc | Pdst | Q | K | V] = act(h[n] . Wp + b)      (groups of 64 columns, see eqd_layer_params)
 // plus, for the tensor-core attention of the same layer, K and V of every node as bf16x3 in 8-node blocks
-//   kv[split][which][n/8][d/8][n%8][d%8]   (1 KB per 8 nodes; a run of blocks is a ready UMMA B operand).
-// Weight-stationary: the 5x3 bf16 panels (120 KB) sit in shared memory for the life of the CTA; two tile
-// groups of 256 threads (2 threads per node row) ping-pong two TMEM accumulators.
+//   kv[which][split][n/8][d/8][n%8][d%8]   (1 KB per 8 nodes; a run of blocks is a ready UMMA B operand).
+// Weight-stationary: the bf16x3 panels (120 KB; 158 KB for the K = 80 layer 0) sit in shared memory for the life of
+// the CTA; two tile groups of 256 threads (2 threads per node row) ping-pong two TMEM accumulators.
 #include "tc_common.cuh"
 
 namespace eqd {
