@@ -68,6 +68,19 @@ class TorchOracle:
 
     @torch.no_grad()
     def forward_pair(self, lig, rec):
+        return self.forward_pair_grad(lig, rec)
+
+    def parameters_for_grad(self):
+        """Turns the weights into autograd leaves (the backward ORACLE of SURVEY 8a 'backward map': parity of any
+        future backward kernels is defined against torch.autograd on this restatement in fp64, itself pinned against
+        the unmodified reference's autograd by tests/golden/*_grads.npz)."""
+        for v in self.sd.values():
+            if v.is_floating_point():
+                v.requires_grad_(True)
+        return self.sd
+
+    def forward_pair_grad(self, lig, rec):
+        """forward_pair without the no_grad guard: outputs stay attached to the weights' autograd graph."""
         sd, dt = self.sd, self.dtype
         emb = sd['iegmn_original.residue_emb_layer.weight']
         sides = []
@@ -96,8 +109,20 @@ class TorchOracle:
         yr_m, yl_m = y_r.mean(0, keepdim=True), y_l.mean(0, keepdim=True)
         A = (y_r - yr_m).t() @ (y_l - yl_m)                                          # :567
         U, S, Vt = torch.linalg.svd(A)                                               # :571
-        corr = torch.diag(torch.tensor([1., 1., float(torch.sign(torch.det(A)))], dtype=dt))  # :586
+        corr = torch.diag(torch.tensor([1., 1., float(torch.sign(torch.det(A.detach())))], dtype=dt))  # :586
         T = (U @ corr) @ Vt
         b = yr_m - (T @ yl_m.t()).t()                                                # :589
         return {'ligand_coors': (T @ l['x0'].t()).t() + b, 'rotation': T, 'translation': b,
                 'keypts_ligand': y_l, 'keypts_receptor': y_r}
+
+
+def probe_loss(coors, y_l, y_r, tgt):
+    """A scalar that exercises every gradient path of the training losses (src/train.py:112-150) without POT: the MSE of
+    the predicted ligand coordinates against a fixed target (train.py:114) plus a transport-like cost of both keypoint
+    sets against fixed points with a CONSTANT plan (the reference detaches its OT plan, ot_utils.py:27), here the
+    seeded weights `w_l`, `w_r`."""
+    t = lambda k: torch.as_tensor(tgt[k]).to(coors.dtype)
+    mse = ((coors - t('coors')) ** 2).mean()
+    ot_l = (t('w_l') * ((y_l - t('p_l')) ** 2).sum(1)).sum() / y_l.shape[0]
+    ot_r = (t('w_r') * ((y_r - t('p_r')) ** 2).sum(1)).sum() / y_r.shape[0]
+    return mse + ot_l + ot_r
