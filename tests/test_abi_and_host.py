@@ -198,3 +198,55 @@ def test_unsupported_configurations_raise():
 
 def test_launch_accounting():
     assert IEGMNEngine.launches_per_forward(8) == 40 and IEGMNEngine.launches_per_forward(5) == 28
+
+
+def _umma_decode(flat, n, k):
+    """Inverse of engine.umma_bf16x3: 3 bf16 splits in the K-major no-swizzle core-matrix layout -> fp32 [n][k]
+    (element (n,k) of a split at (k/8)*n*8 + (n/8)*64 + (n%8)*8 + (k%8) bf16 elements)."""
+    parts = flat.view(3, k // 8, n // 8, 8, 8).float()          # [split][k/8][n/8][n%8][k%8]
+    return parts.sum(0).permute(1, 2, 0, 3).reshape(n, k)
+
+
+@pytest.mark.parametrize('ds,li', [('dips', 0), ('dips', 2), ('db5', 0), ('db5', 1)])
+def test_tensor_core_panels_decode_to_the_reference_weights(ds, li):
+    """The bf16x3 UMMA panels the tensor-core kernels read (edge stage, projections, node MLP; 64-wide layers and the
+    69-wide layer 0 with its K = 80 padding, folded h/h0 blocks and the [K5|V5|Q5] group) reproduce the nn.Linear
+    weights of the checkpoint to 3-term bf16 precision (2^-24 relative)."""
+    sd = {k: torch.from_numpy(v) for k, v in gio.load_checkpoint(ds).items()}
+    pre = f'iegmn_original.iegmn_layers.{li}.'
+    w = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+    P = PackedLayer(w, torch.device('cpu'), 0.75, 0.0, 0.01)
+    dh = P.dh
+    close = lambda a, b: float((a - b).abs().max()) <= 2e-7 * max(1.0, float(b.abs().max()))
+    # edge stage: [W1e (64 x 48) | stacked [W2 ; W3 W2] (128 x 64)]
+    e = P.t['w_edge_tc'].view(torch.bfloat16) if P.t['w_edge_tc'].dtype != torch.bfloat16 else P.t['w_edge_tc']
+    w1e = _umma_decode(e[:3 * 64 * 48], 64, 48)
+    assert close(w1e[:, :42], w['edge_mlp.0.weight'][:, 2 * dh:]) and float(w1e[:, 42:].abs().max()) == 0.0
+    w23 = _umma_decode(e[3 * 64 * 48:], 128, 64)
+    assert close(w23[:64], w['edge_mlp.4.weight'])
+    assert close(w23[64:], (w['coors_mlp.0.weight'].double() @ w['edge_mlp.4.weight'].double()).float())
+    pj, nd = P.t['w_proj_tc'], P.t['w_node_tc']
+    w1, w5, w6 = w['edge_mlp.0.weight'], w['node_mlp.0.weight'], w['node_mlp.4.weight']
+    wq, wk, wv = w['att_mlp_Q.0.weight'], w['att_mlp_K.0.weight'], w['att_mlp_V.0.weight']
+    if dh == 64:
+        groups = [w1[:, :64], w1[:, 64:128], wq, wk, wv]
+        for gi, ref in enumerate(groups):
+            assert close(_umma_decode(pj[gi * 3 * 4096:(gi + 1) * 3 * 4096], 64, 64), ref)
+        w5d = _umma_decode(nd[:3 * 64 * 272], 64, 272)
+        assert close(w5d[:, :261], w5) and float(w5d[:, 261:].abs().max()) == 0.0
+        assert close(_umma_decode(nd[3 * 64 * 272:], 64, 64), w6)
+    else:   # layer 0: K = 80
+        g64 = 3 * 64 * 80
+        refs = [w1[:, :69], w1[:, 69:138], wq[:64], wk[:64], wv[:64]]
+        for gi, ref in enumerate(refs):
+            d = _umma_decode(pj[gi * g64:(gi + 1) * g64], 64, 80)
+            assert close(d[:, :69], ref) and float(d[:, 69:].abs().max()) == 0.0
+        x = _umma_decode(pj[5 * g64:], 16, 80)[:, :69]
+        assert close(x[0:4], wk[64:68]) and close(x[4:8], wv[64:68]) and close(x[8], wk[68]) and close(x[9], wv[68])
+        assert close(x[10:15], wq[64:69]) and float(x[15].abs().max()) == 0.0
+        w5d = _umma_decode(nd[:3 * 80 * 224], 80, 224)
+        assert close(w5d[:69, 0:69], (w5[:, 0:69].double() + w5[:, 202:271].double()).float())   # h and h0 blocks folded
+        assert close(w5d[:69, 80:144], w5[:, 69:133]) and close(w5d[:69, 144:213], w5[:, 133:202])
+        assert float(w5d[69:].abs().max()) == 0.0 and float(w5d[:, 69:80].abs().max()) == 0.0
+        w6d = _umma_decode(nd[3 * 80 * 224:], 64, 80)
+        assert close(w6d[:, :69], w6) and float(w6d[:, 69:].abs().max()) == 0.0
