@@ -11,9 +11,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libeqd_iegmn.so')
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 EDGE_FEATS, N_RBF, HID, H0, H0_PAD, N_RES_TYPES, HEADS, TILE_ROWS = 27, 15, 64, 69, 72, 21, 50, 128
-STATUS_SVD_DEGENERATE, STATUS_NAN, STATUS_DEGREE_OVERFLOW = 1, 2, 4
+STATUS_SVD_DEGENERATE, STATUS_NAN, STATUS_DEGREE_OVERFLOW, STATUS_BAD_RESIDUE = 1, 2, 4, 8
 
 _vp, _i32, _f32 = C.c_void_p, C.c_int32, C.c_float
 
@@ -53,6 +53,7 @@ PROTOTYPES = {
     'eqd_abi_version': (C.c_int, []),
     'eqd_workspace_bytes': (C.c_size_t, [_i32, _i32, _i32]),
     'eqd_embed': (C.c_int, [_G, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'eqd_embed_checked': (C.c_int, [_G, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'eqd_project': (C.c_int, [_G, _L, _vp, _i32, _vp, _vp]),
     'eqd_edge_stage': (C.c_int, [_G, _L, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'eqd_edge_stage_ffma': (C.c_int, [_G, _L, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -317,7 +317,7 @@ static int launch_attention_tc(const eqd_graph* g, const float* proj, int pw, co
   if (reinterpret_cast<uintptr_t>(kv) & 15) return EQD_ERR_BAD_ARG;
   if (g->n_node_tiles <= 0) return EQD_OK;
   size_t smem = sizeof(eqd::AtSmem<X5>) + 128;
-  cudaFuncSetAttribute(eqd::attention_tc_kernel<X5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  EQD_SET_SMEM((eqd::attention_tc_kernel<X5>), smem);
   int grid = (g->n_node_tiles + 1) / 2;
   if (grid > 148) grid = 148;
   long split_stride = (long)((g->n_nodes + 7) / 8 + 8) * 1024;

@@ -24,6 +24,21 @@
     if (e__ != cudaSuccess) return -(1000 + (int)e__);   \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (call site = kernel instantiation, device) instead of on
+// every launch; re-issued only if a larger size is ever requested.  A benign race between host threads at worst sets
+// the same value twice.
+#define EQD_SET_SMEM(kernel, bytes)                                                                            \
+  do {                                                                                                         \
+    static int eqd_smem_set_[64];                                                                              \
+    int dev__ = 0;                                                                                             \
+    cudaGetDevice(&dev__);                                                                                     \
+    if (dev__ < 0 || dev__ >= 64 || eqd_smem_set_[dev__] < (int)(bytes)) {                                     \
+      cudaError_t e__ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+      if (e__ != cudaSuccess) return -(1000 + (int)e__);                                                       \
+      if (dev__ >= 0 && dev__ < 64) eqd_smem_set_[dev__] = (int)(bytes);                                       \
+    }                                                                                                          \
+  } while (0)
+
 namespace eqd {
 
 // ---- optional flight recorder (builds with -DEQD_TRACE only; scripts/hang_trace.py) -------------------------------

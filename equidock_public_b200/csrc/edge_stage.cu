@@ -193,7 +193,7 @@ extern "C" int eqd_edge_stage_ffma(const eqd_graph* g, const eqd_layer_params* p
   if (tn > EQD_TM) tn = EQD_TM;
   int ntiles = (g->n_nodes + tn - 1) / tn;
   size_t smem = sizeof(eqd::EdgeSmem);
-  cudaFuncSetAttribute(eqd::edge_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  EQD_SET_SMEM((eqd::edge_stage_kernel), smem);
   int grid = ntiles < 148 * 2 ? ntiles : 148 * 2;
   eqd::edge_stage_kernel<<<grid, EQD_THREADS, smem, (cudaStream_t)stream>>>(*g, *p, proj, x_in, x_orig, aggr, x_out,
                                                                            status, tn);

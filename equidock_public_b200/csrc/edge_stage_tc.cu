@@ -439,7 +439,7 @@ extern "C" int eqd_edge_stage(const eqd_graph* g, const eqd_layer_params* p, con
   eqd::EdgeConsts cst;
   memcpy(&cst, p->edge_consts_host, sizeof(cst));
   size_t smem = sizeof(eqd::TcSmem) + 128;
-  cudaFuncSetAttribute(eqd::edge_stage_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  EQD_SET_SMEM((eqd::edge_stage_tc_kernel), smem);
   int grid = (ntiles + 1) / 2;
   if (grid > 148) grid = 148;
   eqd::edge_stage_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(*g, *p, cst, proj, x_in, x_orig, aggr, x_out,

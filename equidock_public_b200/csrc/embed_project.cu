@@ -7,7 +7,8 @@ namespace eqd {
 __global__ void embed_kernel(eqd_graph g, const float* __restrict__ emb, const float* __restrict__ res_l,
                              const float* __restrict__ res_r, const float* __restrict__ mu_l,
                              const float* __restrict__ mu_r, const float* __restrict__ x_l,
-                             const float* __restrict__ x_r, float* __restrict__ h0, double* __restrict__ x64) {
+                             const float* __restrict__ x_r, float* __restrict__ h0, double* __restrict__ x64,
+                             int32_t* __restrict__ status) {
   TRACE_START(4);
   const int per_node = EQD_H0_PAD / 4;  // 18 float4 per node
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -20,6 +21,9 @@ __global__ void embed_kernel(eqd_graph g, const float* __restrict__ emb, const f
   if (q < 16) {
     // .view(-1).long() truncation of the fp32-encoded residue index (:460)
     int r = (int)(lig ? res_l[ln] : res_r[ln]);
+    // nn.Embedding raises on an index outside [0, 21): flag it (the host raises in resolve_status); the clamp only
+    // keeps this launch memory-safe
+    if ((r < 0 || r >= EQD_N_RES_TYPES) && status && q == 0) atomicOr(status + g.n_pairs, EQD_STATUS_BAD_RESIDUE);
     r = min(max(r, 0), EQD_N_RES_TYPES - 1);
     v = *reinterpret_cast<const float4*>(emb + r * 64 + q * 4);
   } else {
@@ -65,18 +69,24 @@ __global__ void __launch_bounds__(EQD_THREADS) project_kernel(eqd_graph g, eqd_l
 
 EQD_TRACE_SETTER(eqd_trace_set_embed)
 
-extern "C" int eqd_embed(const eqd_graph* g, const float* emb, const float* res_feat_lig, const float* res_feat_rec,
-                         const float* mu_lig, const float* mu_rec, const float* x_lig, const float* x_rec, float* h0,
-                         double* x64, void* stream) {
+extern "C" int eqd_embed_checked(const eqd_graph* g, const float* emb, const float* res_feat_lig,
+                                 const float* res_feat_rec, const float* mu_lig, const float* mu_rec, const float* x_lig,
+                                 const float* x_rec, float* h0, double* x64, int32_t* status, void* stream) {
   if (!g || !emb || !h0 || !x64) return EQD_ERR_BAD_ARG;
   if (g->n_nodes <= 0) return EQD_OK;
   long total = (long)g->n_nodes * (EQD_H0_PAD / 4);
   int block = 256;
   long grid = (total + block - 1) / block;
   eqd::embed_kernel<<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(*g, emb, res_feat_lig, res_feat_rec, mu_lig,
-                                                                        mu_rec, x_lig, x_rec, h0, x64);
+                                                                        mu_rec, x_lig, x_rec, h0, x64, status);
   EQD_CUDA_LAUNCH_CHECK();
   return EQD_OK;
+}
+
+extern "C" int eqd_embed(const eqd_graph* g, const float* emb, const float* res_feat_lig, const float* res_feat_rec,
+                         const float* mu_lig, const float* mu_rec, const float* x_lig, const float* x_rec, float* h0,
+                         double* x64, void* stream) {
+  return eqd_embed_checked(g, emb, res_feat_lig, res_feat_rec, mu_lig, mu_rec, x_lig, x_rec, h0, x64, nullptr, stream);
 }
 
 extern "C" int eqd_project(const eqd_graph* g, const eqd_layer_params* p, const float* h, int32_t ldh, float* proj,
@@ -89,10 +99,10 @@ extern "C" int eqd_project(const eqd_graph* g, const eqd_layer_params* p, const 
   size_t smem = (size_t)(EQD_TM * (p->dhp + 4) + 2 * EQD_WCHUNK * EQD_WLD) * sizeof(float);
   int grid = ntiles < 148 * 4 ? ntiles : 148 * 4;
   if (p->dhp == 72) {
-    cudaFuncSetAttribute(eqd::project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    EQD_SET_SMEM((eqd::project_kernel<true>), smem);
     eqd::project_kernel<true><<<grid, EQD_THREADS, smem, (cudaStream_t)stream>>>(*g, *p, h, ldh, proj);
   } else {
-    cudaFuncSetAttribute(eqd::project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    EQD_SET_SMEM((eqd::project_kernel<false>), smem);
     eqd::project_kernel<false><<<grid, EQD_THREADS, smem, (cudaStream_t)stream>>>(*g, *p, h, ldh, proj);
   }
   EQD_CUDA_LAUNCH_CHECK();

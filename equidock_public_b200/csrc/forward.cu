@@ -87,14 +87,17 @@ extern "C" int eqd_iegmn_forward(const eqd_graph* g, const eqd_layer_params* con
   // blocks of each (K|V, split) plane, and the pad rows of x5 (they reach P.V as 0 x value: must be finite)
   if (!(dbg & 2)) {
     const size_t plane = c.kv_bytes / 6, from = (size_t)(N / 8) * 1024;
-    for (int pl = 0; pl < 6; ++pl) cudaMemsetAsync(kv + pl * plane + from, 0, plane - from, st);
-    cudaMemsetAsync(x5 + (size_t)N * 16, 0, (c.x5_rows - (size_t)N) * 16 * 4, st);
-    cudaMemsetAsync(io->status, 0, (size_t)(B + 1) * sizeof(int32_t), st);
+    cudaError_t me = cudaSuccess;
+    for (int pl = 0; pl < 6 && me == cudaSuccess; ++pl) me = cudaMemsetAsync(kv + pl * plane + from, 0, plane - from, st);
+    if (me == cudaSuccess) me = cudaMemsetAsync(x5 + (size_t)N * 16, 0, (c.x5_rows - (size_t)N) * 16 * 4, st);
+    if (me == cudaSuccess) me = cudaMemsetAsync(io->status, 0, (size_t)(B + 1) * sizeof(int32_t), st);
+    if (me != cudaSuccess) return -(1000 + (int)me);
   }
   auto stage_event = [&](int li, int which) {   // which: 0 edge begin, 1 edge end, 2 node begin, 3 node end
     if (io->stage_events && io->stage_events[li * 4 + which]) cudaEventRecord((cudaEvent_t)io->stage_events[li * 4 + which], st);
   };
-  int rc = eqd_embed(g, io->emb, io->res_lig, io->res_rec, io->mu_lig, io->mu_rec, io->x_lig, io->x_rec, h0, x0, stream);
+  int rc = eqd_embed_checked(g, io->emb, io->res_lig, io->res_rec, io->mu_lig, io->mu_rec, io->x_lig, io->x_rec, h0, x0,
+                             io->status, stream);
   if (rc) return rc;
   const eqd_layer_params* l0 = layers[0];
   const bool tc0 = l0->dh == EQD_H0 && l0->w_proj_tc && l0->w_node_tc && !io->layer0_fp32;

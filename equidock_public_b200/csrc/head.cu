@@ -480,7 +480,7 @@ extern "C" int eqd_keypoints(const eqd_graph* g, const eqd_head_params* hp, cons
   const int nseg = 2 * g->n_pairs;
   {
     size_t smem = (size_t)(EQD_TM * 68 + 2 * EQD_WCHUNK * EQD_WLD) * sizeof(float);
-    cudaFuncSetAttribute(eqd::head_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    EQD_SET_SMEM((eqd::head_mean_kernel), smem);
     int grid = g->n_node_tiles < 148 * 2 ? g->n_node_tiles : 148 * 2;
     eqd::head_mean_kernel<<<grid, EQD_THREADS, smem, st>>>(*g, *hp, h, part);
     EQD_CUDA_LAUNCH_CHECK();
@@ -497,7 +497,7 @@ extern "C" int eqd_keypoints(const eqd_graph* g, const eqd_head_params* hp, cons
   }
   {
     size_t smem = sizeof(eqd::KeypSmem);
-    cudaFuncSetAttribute(eqd::keypoints_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    EQD_SET_SMEM((eqd::keypoints_kernel), smem);
     eqd::keypoints_kernel<<<dim3(2 * g->n_pairs, EQD_HEADS / KP_HEADS_PER_CTA), KP_THREADS, smem, st>>>(*g, h, x, u, keypts);
     EQD_CUDA_LAUNCH_CHECK();
   }

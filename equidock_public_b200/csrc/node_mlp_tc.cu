@@ -493,7 +493,7 @@ extern "C" int eqd_node_mlp_tc(const eqd_graph* g, const eqd_layer_params* p, co
   memcpy(&cst, p->node_consts_host, sizeof(cst));
   int ntiles = (g->n_nodes + EQD_TM - 1) / EQD_TM;
   size_t smem = sizeof(eqd::NmSmem) + 128;
-  cudaFuncSetAttribute(eqd::node_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  EQD_SET_SMEM((eqd::node_mlp_tc_kernel), smem);
   int grid = (ntiles + 1) / 2;
   if (grid > 148) grid = 148;
   eqd::node_mlp_tc_kernel<<<grid, NM_THREADS, smem, (cudaStream_t)stream>>>(g->n_nodes, *p, cst, h_in, aggr, mu, h0, h_out);
@@ -512,7 +512,7 @@ extern "C" int eqd_node_mlp_tc0(const eqd_graph* g, const eqd_layer_params* p, c
   memcpy(&cst, p->node_consts_host, sizeof(cst));
   int ntiles = (g->n_nodes + EQD_TM - 1) / EQD_TM;
   size_t smem = sizeof(eqd::Nm0Smem) + 128;
-  cudaFuncSetAttribute(eqd::node_mlp0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  EQD_SET_SMEM((eqd::node_mlp0_tc_kernel), smem);
   int grid = (ntiles + 1) / 2;
   if (grid > 148) grid = 148;
   eqd::node_mlp0_tc_kernel<<<grid, NM_THREADS, smem, (cudaStream_t)stream>>>(g->n_nodes, *p, cst, h0, aggr, mu, h_out);

@@ -264,7 +264,7 @@ static int launch_project_tc(const eqd_graph* g, const eqd_layer_params* p, cons
   memcpy(&cst, p->proj_bias_host, 320 * sizeof(float));
   int ntiles = (g->n_nodes + EQD_TM - 1) / EQD_TM;
   size_t smem = sizeof(eqd::PjSmem<L0>) + 128;
-  cudaFuncSetAttribute(eqd::project_tc_kernel<L0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  EQD_SET_SMEM((eqd::project_tc_kernel<L0>), smem);
   int grid = (ntiles + 1) / 2;
   if (grid > 148) grid = 148;
   long split_stride = (long)((g->n_nodes + 7) / 8 + 8) * 1024;

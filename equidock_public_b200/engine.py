@@ -21,6 +21,31 @@ def _dev_f32(t, device):
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
+def _host_f32(t):
+    return t.detach().to(device='cpu', dtype=torch.float32).contiguous()
+
+
+def _upload_blob(tensors: Dict[str, torch.Tensor], device) -> Dict[str, torch.Tensor]:
+    """Packs host tensors (fp32 / bf16) into ONE 256-byte-aligned byte blob, uploads it with a single H2D copy and
+    returns device views.  All weight repacking happens on the host: the only GPU work of a (re)pack is one memcpy, so
+    no ATen kernel of a repack ever appears among the engine's kernels."""
+    offs, total = {}, 0
+    for k, t in tensors.items():
+        offs[k] = total
+        total += (t.numel() * t.element_size() + 255) & ~255
+    host = torch.zeros(max(total, 256), dtype=torch.uint8)
+    for k, t in tensors.items():
+        n = t.numel() * t.element_size()
+        host[offs[k]:offs[k] + n] = t.contiguous().view(-1).view(torch.uint8)
+    dev = host.to(device)
+    out = {}
+    for k, t in tensors.items():
+        n = t.numel() * t.element_size()
+        out[k] = dev[offs[k]:offs[k] + n].view(t.dtype).view(t.shape)
+    out['_blob'] = dev
+    return out
+
+
 def umma_bf16x3(w: torch.Tensor) -> torch.Tensor:
     """[N][K] fp32 weight (nn.Linear layout, K % 8 == 0) -> 3 bf16 splits (w ~ w0+w1+w2, round to nearest), each in
     the UMMA canonical K-major no-swizzle layout: element (n,k) at (k/8)*N*16 + (n/8)*128 + (n%8)*16 + (k%8)*2 bytes.
@@ -47,7 +72,7 @@ class PackedLayer:
 
     def __init__(self, sd: Dict[str, torch.Tensor], device, skip_weight_h: float, x_connection_init: float,
                  leaky_slope: float):
-        f = lambda k: _dev_f32(sd[k], device)
+        f = lambda k: _host_f32(sd[k])      # everything below is host arithmetic; ONE upload at the end
         w1, b1 = f('edge_mlp.0.weight'), f('edge_mlp.0.bias')
         wq, wk, wv = f('att_mlp_Q.0.weight'), f('att_mlp_K.0.weight'), f('att_mlp_V.0.weight')
         w5, b5 = f('node_mlp.0.weight'), f('node_mlp.0.bias')
@@ -58,7 +83,7 @@ class PackedLayer:
         dhp = nat.HID if dh == nat.HID else nat.H0_PAD
         n_e = nat.EDGE_FEATS + nat.N_RBF
         assert w1.shape == (nat.HID, 2 * dh + n_e) and w5.shape == (dh, 2 * dh + nat.HID + nat.H0)
-        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32)
         pw = 128 + 3 * dhp
         w_proj, b_proj = z(dhp, pw), z(pw)
         w_proj[:dh, 0:64] = w1[:, 0:dh].t()
@@ -117,7 +142,7 @@ class PackedLayer:
             pb = z(320)
             pb[64:128] = b1
             self.proj_bias_host = pb.cpu().contiguous()
-        self.t = {
+        self.t = _upload_blob({
             **tc,
             'w_proj': w_proj, 'b_proj': b_proj, 'w_edge1': w_edge1,
             'edge_ln_g': f('edge_mlp.3.weight'), 'edge_ln_b': f('edge_mlp.3.bias'),
@@ -127,11 +152,12 @@ class PackedLayer:
             'w_node1': w_node1, 'b_node1': pad(b5),
             'node_ln_g': pad(f('node_mlp.3.weight')), 'node_ln_b': pad(f('node_mlp.3.bias')),
             'w_node2': w_node2, 'b_node2': b6, 'w_edge_tc': w_edge_tc,
-        }
+        }, device)
         s = nat.EqdLayerParams()
         s.dh, s.dhp = dh, dhp
         for k, v in self.t.items():
-            setattr(s, k, v.data_ptr())
+            if not k.startswith('_'):
+                setattr(s, k, v.data_ptr())
         s.edge_consts_host = self.edge_consts_host.data_ptr()
         if self.node_consts_host is not None:
             s.node_consts_host = self.node_consts_host.data_ptr()
@@ -143,12 +169,13 @@ class PackedLayer:
 
 class PackedHead:
     def __init__(self, w_mean, b_mean, w_key, w_query, device, leaky_slope: float):
-        self.t = {'w_mean': _dev_f32(w_mean, device).t().contiguous(), 'b_mean': _dev_f32(b_mean, device),
-                  'w_key': _dev_f32(w_key, device), 'w_query': _dev_f32(w_query, device)}
+        self.t = _upload_blob({'w_mean': _host_f32(w_mean).t().contiguous(), 'b_mean': _host_f32(b_mean),
+                               'w_key': _host_f32(w_key), 'w_query': _host_f32(w_query)}, device)
         assert self.t['w_key'].shape == (nat.HEADS * nat.HID, nat.HID)
         s = nat.EqdHeadParams()
         for k, v in self.t.items():
-            setattr(s, k, v.data_ptr())
+            if not k.startswith('_'):
+                setattr(s, k, v.data_ptr())
         s.leaky_slope = leaky_slope
         self.struct = s
         # weights-only fold of the 50-head key / query projections (eqd_head_fold), done once per model on the device
@@ -157,6 +184,26 @@ class PackedHead:
             nat.check(nat.load().eqd_head_fold(C.byref(s), self.m_qk.data_ptr(), torch.cuda.current_stream().cuda_stream),
                       'eqd_head_fold')
         s.m_qk = self.m_qk.data_ptr()
+
+
+def _aligned_he(he, device):
+    """The edge-feature matrix as the edge kernels need it: fp32, contiguous, 16-byte aligned base and readable up to the
+    next 16-byte boundary past its end (TMA bulk copies over-read the last row).  A caller's tensor that already satisfies
+    this is used in place (no copy of the largest input); row slices of a batched ``he`` (``dgl.unbatch`` /
+    ``hetero_graph.unbatch``: offset = first_edge * 108 bytes) generally do not and are copied into an owned, padded
+    buffer."""
+    he = he.to(device=device, dtype=torch.float32).contiguous()
+    nbytes = he.numel() * 4
+    try:
+        room = he.untyped_storage().nbytes() - he.storage_offset() * 4
+    except RuntimeError:
+        room = nbytes
+    if he.data_ptr() % 16 == 0 and room >= ((nbytes + 15) & ~15):
+        return he
+    buf = torch.empty(((nbytes + 15) // 16) * 4 + 4, dtype=torch.float32, device=device)
+    own = buf[:he.numel()].view(he.shape)
+    own.copy_(he)
+    return own
 
 
 class GraphPlan:
@@ -185,11 +232,12 @@ class GraphPlan:
         # read together with the per-pair status (one sync per forward).
         d64 = self.edge_dst.long()
         self.unsorted = ((d64[1:] < d64[:-1]).any() if self.E > 1 else torch.zeros((), dtype=torch.bool, device=device))
+        self.unsorted_i32 = self.unsorted.to(torch.int32).reshape(1)
+        self._arange = None
         # row_ptr[n] = first edge whose destination is >= n.  searchsorted on the (sorted) destination list needs no
         # host sync -- torch.bincount would block the CPU on the previous batch and break the copy/compute overlap.
         self.row_ptr = torch.searchsorted(self.edge_dst, torch.arange(self.N + 1, **i32), out_int32=True).contiguous()
-        self.he_l = he_l.to(device=device, dtype=torch.float32).contiguous()
-        self.he_r = he_r.to(device=device, dtype=torch.float32).contiguous()
+        self.he_l, self.he_r = _aligned_he(he_l, device), _aligned_he(he_r, device)
         assert self.he_l.shape == (self.E_l, nat.EDGE_FEATS) and self.he_r.shape == (self.E_r, nat.EDGE_FEATS)
         seg = np.zeros(2 * self.n_pairs + 1, dtype=np.int64)
         seg[1:] = np.cumsum(np.asarray(n_lig + n_rec, dtype=np.int64))
@@ -214,6 +262,34 @@ class GraphPlan:
         g.n_node_tiles, g.node_tiles = self.n_node_tiles, self.node_tiles.data_ptr()
         self.struct = g
 
+    def refresh(self, graph) -> bool:
+        """Re-derives the topology arrays IN PLACE from a graph object whose tensors were overwritten with a new batch
+        of the same shape signature (same per-pair node counts and edge totals): every device pointer of the plan stays
+        valid, which is what a captured CUDA graph of the forward needs.  Returns False when the shapes differ (the
+        caller must build a new plan).  A handful of index ops on the current stream, no host sync."""
+        n_l = [int(v) for v in graph.batch_num_nodes(LIGAND).tolist()]
+        n_r = [int(v) for v in graph.batch_num_nodes(RECEPTOR).tolist()]
+        src_l, dst_l = graph.edges(etype=LL)
+        src_r, dst_r = graph.edges(etype=RR)
+        if (n_l != self.n_lig_list or n_r != self.n_rec_list or int(src_l.shape[0]) != self.E_l
+                or int(src_r.shape[0]) != self.E_r):
+            return False
+        E_l = self.E_l
+        self.col_src[:E_l].copy_(src_l)
+        torch.add(src_r, self.N_l, out=self.col_src[E_l:])
+        self.edge_dst[:E_l].copy_(dst_l)
+        torch.add(dst_r, self.N_l, out=self.edge_dst[E_l:])
+        if self.E > 1:
+            torch.any(self.edge_dst[1:] < self.edge_dst[:-1], dim=0, keepdim=True, out=self.unsorted.view(1))
+        self.unsorted_i32.copy_(self.unsorted.view(1))
+        if self._arange is None:
+            self._arange = torch.arange(self.N + 1, dtype=torch.int32, device=self.device)
+        torch.searchsorted(self.edge_dst, self._arange, out_int32=True, out=self.row_ptr)
+        for own, new in ((self.he_l, graph.edges[LL].data['he']), (self.he_r, graph.edges[RR].data['he'])):
+            if own.data_ptr() != new.data_ptr():
+                own.copy_(new)
+        return True
+
     @classmethod
     def from_graph(cls, graph, device, max_in_degree: int = 10) -> 'GraphPlan':
         """From a batched DGL heterograph (train_utils.py:61-100) or a ``PairGraphBatch``."""
@@ -236,19 +312,51 @@ def _sorted_copy(plan_args):
     return n_l, n_r, sl, dl, sr, dr, hl, hr, device, mid
 
 
-_STATUS_RING = {'bufs': [], 'next': 0}
+class _StatusPool:
+    """Pinned int32 buffers for the per-forward status words, owned by exactly one pending forward at a time: taken from
+    a free list by ``forward`` and handed back by ``resolve_status`` (or by the garbage collector if a caller drops an
+    unresolved handle), so any number of forwards may be in flight without one overwriting another's flags.  Allocating
+    page-locked memory per call (cudaHostAlloc) would stall the CPU for tens of milliseconds every few steps."""
+
+    def __init__(self):
+        import threading
+        self.free, self.lock = [], threading.Lock()
+
+    def take(self, n: int) -> torch.Tensor:
+        with self.lock:
+            for i, b in enumerate(self.free):
+                if b.numel() >= n:
+                    return self.free.pop(i)
+        return torch.empty(max(n, 1024), dtype=torch.int32, pin_memory=True)
+
+    def give(self, buf: torch.Tensor):
+        with self.lock:
+            if len(self.free) < 64:
+                self.free.append(buf)
 
 
-def _pinned_status(n: int) -> torch.Tensor:
-    """A pinned int32 buffer from a small ring (8 deep: more than the number of forwards ever in flight).  Allocating
-    page-locked memory per call (cudaHostAlloc) stalls the CPU for tens of milliseconds every few steps."""
-    ring = _STATUS_RING
-    if not ring['bufs'] or ring['bufs'][0].numel() < n:
-        ring['bufs'] = [torch.empty(max(n, 1024), dtype=torch.int32, pin_memory=True) for _ in range(8)]
-        ring['next'] = 0
-    buf = ring['bufs'][ring['next'] % 8]
-    ring['next'] += 1
-    return buf[:n]
+_STATUS_POOL = _StatusPool()
+
+
+class _StatusLease:
+    """Returns its pinned buffer to the pool when released (explicitly after the status was read, or on GC)."""
+
+    def __init__(self, n):
+        self.buf, self.n = _STATUS_POOL.take(n), n
+
+    def view(self):
+        return self.buf[:self.n]
+
+    def release(self):
+        if self.buf is not None:
+            _STATUS_POOL.give(self.buf)
+            self.buf = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 class NativeStageTimer:
@@ -256,10 +364,18 @@ class NativeStageTimer:
     stream; in the Python driver the same handles are recorded through begin() / end()."""
 
     def __init__(self):
-        self.lib, self.sets = nat.load(), []
+        self.lib, self.sets, self.spare = nat.load(), [], []
+
+    def reserve(self, n_forwards, n_layers):
+        """Creates the events of `n_forwards` forwards up front, so that a timed loop creates none."""
+        for _ in range(n_forwards):
+            self.spare.append((C.c_void_p * (4 * n_layers))(*[self.lib.eqd_event_create() for _ in range(4 * n_layers)]))
 
     def new_forward(self, n_layers):
-        arr = (C.c_void_p * (4 * n_layers))(*[self.lib.eqd_event_create() for _ in range(4 * n_layers)])
+        if self.spare and len(self.spare[-1]) == 4 * n_layers:
+            arr = self.spare.pop()
+        else:
+            arr = (C.c_void_p * (4 * n_layers))(*[self.lib.eqd_event_create() for _ in range(4 * n_layers)])
         self.sets.append(arr)
         return arr
 
@@ -278,10 +394,10 @@ class NativeStageTimer:
         return float(sum(x for x in (self.lib.eqd_event_elapsed_ms(a, b) for a, b in self._pairs(name)) if x >= 0))
 
     def close(self):
-        for arr in self.sets:
+        for arr in self.sets + self.spare:
             for e in arr:
                 self.lib.eqd_event_destroy(e)
-        self.sets = []
+        self.sets, self.spare = [], []
 
 
 class IEGMNEngine:
@@ -306,13 +422,19 @@ class IEGMNEngine:
 
     def forward(self, plan: GraphPlan, emb: torch.Tensor, layers: List[PackedLayer], head: PackedHead,
                 res_l, res_r, mu_l, mu_r, x_l, x_r, check_status: bool = True, log=None,
-                stage_timer=None) -> Dict[str, torch.Tensor]:
+                stage_timer=None, record_event: bool = True) -> Dict[str, torch.Tensor]:
         """One forward = ONE call into the library (eqd_iegmn_forward): the per-stage entry points are chained in C on
         the current stream out of a single workspace allocation.  EQD_PY_FORWARD=1 selects the stage-by-stage Python
         driver below instead (same kernels; used to A/B the two and by the per-stage tests)."""
-        if _PY_FORWARD:
-            return self._forward_py(plan, emb, layers, head, res_l, res_r, mu_l, mu_r, x_l, x_r, check_status, log,
-                                    stage_timer)
+        with torch.cuda.device(self.device):   # the raw launches below go to the CURRENT device: make it the model's
+            if _PY_FORWARD:
+                return self._forward_py(plan, emb, layers, head, res_l, res_r, mu_l, mu_r, x_l, x_r, check_status, log,
+                                        stage_timer)
+            return self._forward_native(plan, emb, layers, head, res_l, res_r, mu_l, mu_r, x_l, x_r, check_status, log,
+                                        stage_timer, record_event)
+
+    def _forward_native(self, plan, emb, layers, head, res_l, res_r, mu_l, mu_r, x_l, x_r, check_status, log,
+                        stage_timer, record_event=True):
         lib, dev = self.lib, self.device
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         N, B = plan.N, plan.n_pairs
@@ -346,14 +468,17 @@ class IEGMNEngine:
         kab = lambda mask: nat.check(lib.eqd_kabsch_apply(
             g, nat.ptr(cov), nat.ptr(ymean), nat.ptr(x_l), nat.ptr(mask), nat.ptr(rot), nat.ptr(trans),
             nat.ptr(lig_out), nat.ptr(sing), nat.ptr(status), st), 'eqd_kabsch_apply')
-        status_host = _pinned_status(B + 2)
+        lease = _StatusLease(B + 2)
+        status_host = lease.view()
         status_host[:B + 1].copy_(status, non_blocking=True)
-        status_host[B + 1:].copy_(plan.unsorted.to(torch.int32).reshape(1), non_blocking=True)
-        status_event = torch.cuda.Event()
-        status_event.record()
-        out = {'ligand_coors': lig_out, 'keypts': keyp, 'rotation': rot, 'translation': trans, 'h': h_fin,
-               'x64': x_fin, 'cov': cov, 'sing': sing, 'status': status, 'unsorted': plan.unsorted, 'kabsch': kab,
-               'status_host': status_host, 'status_event': status_event, '_keep': (ws, ymean, x_l)}
+        status_host[B + 1:].copy_(plan.unsorted_i32, non_blocking=True)
+        status_event = None
+        if record_event:     # (a CUDA-graph capture records its own event after every replay instead)
+            status_event = torch.cuda.Event()
+            status_event.record()
+        out = {'status_lease': lease, 'ligand_coors': lig_out, 'keypts': keyp, 'rotation': rot, 'translation': trans,
+               'h': h_fin, 'x64': x_fin, 'cov': cov, 'sing': sing, 'status': status, 'unsorted': plan.unsorted,
+               'kabsch': kab, 'status_host': status_host, 'status_event': status_event, '_keep': (ws, ymean, x_l)}
         if check_status:
             self.resolve_status(plan, out, kab, log)
         return out
@@ -445,11 +570,13 @@ class IEGMNEngine:
         kab(None)
         # status words -> pinned host memory, asynchronously; resolve_status() waits on the event only, so a caller
         # may launch the next forward before looking at this one's flags (bench.py keeps two steps in flight)
-        status_host = _pinned_status(B + 2)
-        status_host.copy_(torch.cat([status, plan.unsorted.to(torch.int32).reshape(1)]), non_blocking=True)
+        lease = _StatusLease(B + 2)
+        status_host = lease.view()
+        status_host[:B + 1].copy_(status, non_blocking=True)
+        status_host[B + 1:].copy_(plan.unsorted_i32, non_blocking=True)
         status_event = torch.cuda.Event()
         status_event.record()
-        out = {'ligand_coors': lig_out, 'keypts': keyp, 'rotation': rot, 'translation': trans, 'h': h_fin,
+        out = {'status_lease': lease,'ligand_coors': lig_out, 'keypts': keyp, 'rotation': rot, 'translation': trans, 'h': h_fin,
                'x64': x_fin, 'cov': cov, 'sing': sing, 'status': status, 'unsorted': plan.unsorted, 'kabsch': kab,
                'status_host': status_host, 'status_event': status_event}
         if check_status:
@@ -459,10 +586,23 @@ class IEGMNEngine:
     def resolve_status(self, plan: GraphPlan, out, kab, log=None):
         """The ONE host sync of a forward: reads the status words and replays the reference's
         host-side control flow for flagged pairs (rigid_docking_model.py:570-584)."""
+        with torch.cuda.device(self.device):
+            try:
+                self._resolve_status(plan, out, kab, log)
+            finally:
+                lease = out.get('status_lease')
+                if lease is not None:       # the flags have been read (or the call failed): the buffer may be reused
+                    out['status_host'] = out['status_host'].clone()
+                    lease.release()
+
+    def _resolve_status(self, plan: GraphPlan, out, kab, log=None):
         out['status_event'].synchronize()
         st_host = out['status_host']
         if int(st_host[-1]) != 0:
             raise UnsortedEdges()
+        if int(st_host[plan.n_pairs]) & nat.STATUS_BAD_RESIDUE:
+            raise IndexError('res_feat holds a residue index outside [0, 21): index out of range in self '
+                             '(nn.Embedding, rigid_docking_model.py:460)')
         if int(st_host[plan.n_pairs]) & nat.STATUS_DEGREE_OVERFLOW:
             raise nat.NativeLibraryError(
                 f'a node has more than max_in_degree={plan.struct.max_in_degree} in-edges; '

@@ -269,6 +269,8 @@ class IEGMN(nn.Module):
         if not (self.use_edge_features_in_gmn and self.use_mean_node_features):
             raise NotImplementedError('CUDA engine: use_edge_features_in_gmn and use_mean_node_features must be on')
 
+        if int(args['residue_emb_dim']) != nat.HID:
+            raise NotImplementedError(f'CUDA engine: residue_emb_dim must be {nat.HID}')
         self.residue_emb_layer = nn.Embedding(num_embeddings=21, embedding_dim=args['residue_emb_dim'])
         in_dim = args['residue_emb_dim'] + 5  # + mu_r_norm surface features (:387-388)
         hid = args['iegmn_lay_hid_dim']
@@ -310,9 +312,10 @@ class IEGMN(nn.Module):
             self._head_key = key
         return self._head
 
-    def run_engine(self, batch_hetero_graph, check_status=True):
+    def run_engine(self, batch_hetero_graph, check_status=True, record_event=True):
         """The whole hot path on the device; returns the engine's raw output dict.  With ``check_status=False`` the
-        per-pair status words are left pending (``resolve(out)`` finishes the call)."""
+        per-pair status words are left pending (``resolve(out)`` finishes the call).  ``record_event=False`` is for
+        CUDA-graph capture (``graphed.GraphedForward``), which records its own completion event per replay."""
         emb = self.residue_emb_layer.weight
         dev = emb.device
         for lay in self.iegmn_layers:
@@ -324,7 +327,8 @@ class IEGMN(nn.Module):
         plan = _plan_for(batch_hetero_graph, dev, self.graph_max_neighbor)
         emb32 = emb.detach().to(torch.float32).contiguous()
         call = lambda p, chk: eng.forward(p, emb32, layers, head, nl['res_feat'], nr['res_feat'], nl['mu_r_norm'],
-                                          nr['mu_r_norm'], nl['new_x'], nr['x'], chk, self.log)
+                                          nr['mu_r_norm'], nl['new_x'], nr['x'], chk, self.log,
+                                          record_event=record_event)
         try:
             out = call(plan, check_status)
         except UnsortedEdges:
@@ -389,10 +393,21 @@ class Rigid_Body_Docking_Net(nn.Module):
         net, raw = self, self.iegmn_original.run_engine(batch_hetero_graph, check_status=False)
 
         class Pending:
+            def raw_result(self_inner):
+                """The engine's batched output dict (``ligand_coors`` (sum N_l, 3), ``rotation`` (B, 3, 3),
+                ``translation`` (B, 1, 3), ``keypts`` (2B, 50, 3), ...) once the status words are resolved."""
+                return net.iegmn_original.resolve(raw)
+
             def result(self_inner):
                 out = net.iegmn_original.resolve(raw)
                 return net._assemble(net.iegmn_original.package(out, batch_hetero_graph))
         return Pending()
+
+    def graphed(self, device_batch):
+        """A CUDA-graph capture of this model's forward for one fixed-shape device batch (``graphed.GraphedForward``):
+        ``.launch().result()`` returns what ``model(batch, epoch)`` returns at the host cost of one graph launch."""
+        from .graphed import GraphedForward
+        return GraphedForward(self, device_batch)
 
     def forward(self, batch_hetero_graph, epoch):
         return self._assemble(self.iegmn_original(batch_hetero_graph, epoch))

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define EQD_ABI_VERSION 5
+#define EQD_ABI_VERSION 6
 
 #define EQD_EDGE_FEATS 27     /* input_edge_feats_dim, protein_utils.py:71-86 + :373-389 */
 #define EQD_N_RBF 15          /* all_sigmas_dist = 1.5**s, rigid_docking_model.py:116 */
@@ -55,6 +55,7 @@ enum {
 #define EQD_STATUS_NAN 2             /* assert :570 would have failed */
 /* global status bit (status[n_pairs]) */
 #define EQD_STATUS_DEGREE_OVERFLOW 4 /* some node has more than max_in_degree in-edges */
+#define EQD_STATUS_BAD_RESIDUE 8     /* a res_feat index outside [0, 21): nn.Embedding (:460) would raise IndexError */
 
 /* ---- batch topology (all pointers device memory) ------------------------------------------ */
 typedef struct eqd_graph {
@@ -153,6 +154,10 @@ int eqd_embed(const eqd_graph* g, const float* emb /*[21][64]*/,
               const float* mu_lig, const float* mu_rec,               /* [N][5] */
               const float* x_lig /* new_x */, const float* x_rec /* x */, /* [N][3] */
               float* h0, double* x64, void* stream);
+/* Same, and ORs EQD_STATUS_BAD_RESIDUE into status[n_pairs] when a residue index is out of range (status may be NULL). */
+int eqd_embed_checked(const eqd_graph* g, const float* emb, const float* res_feat_lig, const float* res_feat_rec,
+                      const float* mu_lig, const float* mu_rec, const float* x_lig, const float* x_rec,
+                      float* h0, double* x64, int32_t* status /* [n_pairs+1] */, void* stream);
 
 /* Node projections for a layer (see eqd_layer_params.w_proj): proj[n][128+3*dhp]. */
 int eqd_project(const eqd_graph* g, const eqd_layer_params* p, const float* h, int32_t ldh,

