@@ -564,13 +564,14 @@ def run_engine(args, rank, local_rank, world):
                      'issued_bf16_frac': n_edges * EDGE_TC_BF16_FLOP_PER_EDGE / (edge_ms * 1e-3) / 1e12 / tc_peak,
                      'hbm': {'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
                              'algorithmic_bytes_per_launch': alg},
-                     'share_of_step': timer.total_ms('edge_stage') / instr_ms,
+                     'share_of_step': timer.total_ms('edge_stage') / K / step_ms,
+                     'share_of_instrumented_step': timer.total_ms('edge_stage') / instr_ms,
                      'note': 'fp32-accurate GEMMs as 6 bf16 split products on tcgen05 (bf16x6): the tensor ceiling in '
                              'algorithmic fp32 FLOPs is peak x 38272 / 135168 = 0.283 x peak; AI ~290 FLOP/B, so the HBM '
                              'fraction (north star) is small by construction'},
         'kernels_ms': {'edge_stage': edge_ms, 'node_stage': node_ms,
-                       'edge_share': timer.total_ms('edge_stage') / instr_ms,
-                       'node_share': timer.total_ms('node_stage') / instr_ms},
+                       'edge_share': timer.total_ms('edge_stage') / K / step_ms,
+                       'node_share': timer.total_ms('node_stage') / K / step_ms},
     }
     if wl['flop_per_pair']:
         line['step_roofline'] = {'hbm_frac': value / world * wl['bytes_per_pair'] / 1e9 / hbm_peak,
