@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libeqd_iegmn.so')
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 EDGE_FEATS, N_RBF, HID, H0, H0_PAD, N_RES_TYPES, HEADS, TILE_ROWS = 27, 15, 64, 69, 72, 21, 50, 128
 STATUS_SVD_DEGENERATE, STATUS_NAN, STATUS_DEGREE_OVERFLOW, STATUS_BAD_RESIDUE = 1, 2, 4, 8
 
@@ -40,7 +40,7 @@ class EqdLayerParams(C.Structure):
 class EqdForwardIO(C.Structure):
     _fields_ = [(n, _vp) for n in ('emb', 'res_lig', 'res_rec', 'mu_lig', 'mu_rec', 'x_lig', 'x_rec', 'rot', 'trans',
                                    'ligand_out', 'sing', 'status', 'h_out', 'x_out', 'keypts', 'cov', 'ymean', 'stage_events')] + \
-               [('layer0_fp32', _i32)]
+               [('layer0_fp32', _i32), ('train_stash', _vp), ('train_stash_bytes', C.c_size_t)]
 
 
 class EqdHeadParams(C.Structure):
@@ -72,6 +72,23 @@ PROTOTYPES = {
     'eqd_head_fold': (C.c_int, [_H, _vp, _vp]),
     'eqd_forward_workspace_bytes': (C.c_size_t, [_G]),
     'eqd_iegmn_forward': (C.c_int, [_G, C.POINTER(_L), _i32, _H, C.POINTER(EqdForwardIO), _vp, C.c_size_t, _vp]),
+    'eqd_forward_stash_bytes': (C.c_size_t, [_G, _i32]),
+    'eqd_forward_stash_offsets': (C.c_int, [_G, _i32, C.POINTER(C.c_size_t)]),
+    'eqd_tn_partial_floats': (C.c_size_t, [C.c_int64, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
+    'eqd_tn_gemm': (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, C.c_int64, _f32, _vp, _vp, C.POINTER(_i32), _vp]),
+    'eqd_grad_reduce': (C.c_int, [_vp, _i32, C.c_int64, _vp, _vp, _i32, _vp, _vp]),
+    'eqd_bwd_node_mlp': (C.c_int, [_G, _L] + [_vp] * 3 + [_i32, _vp, _vp, _i32] + [_vp] * 9 + [C.POINTER(_i32), _vp]),
+    'eqd_bwd_attention': (C.c_int, [_G, _L, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    'eqd_bwd_edge': (C.c_int, [_G, _L] + [_vp] * 14 + [C.POINTER(_i32), _vp]),
+    'eqd_bwd_edge_gather': (C.c_int, [_G, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _vp]),
+    'eqd_bwd_project': (C.c_int, [_G, _L, _vp, _vp, _vp, _vp]),
+    'eqd_bwd_embed': (C.c_int, [_G, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'eqd_bwd_head_workspace_bytes': (C.c_size_t, [_i32, _i32, _i32]),
+    'eqd_bwd_head': (C.c_int, [_G, _H] + [_vp] * 9 + [C.c_size_t] + [_vp] * 6),
+    'eqd_losses_workspace_bytes': (C.c_size_t, [_i32, _i32]),
+    'eqd_losses': (C.c_int, [_G] + [_vp] * 7 + [_i32, _f32, _f32, _f32, _f32, _vp, C.c_size_t] + [_vp] * 6),
+    'eqd_sqnorm_partials': (C.c_int, [_vp, C.c_int64, _vp, _i32, _vp]),
+    'eqd_clip_adam': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp, _vp]),
     'eqd_event_create': (_vp, []),
     'eqd_event_destroy': (None, [_vp]),
     'eqd_event_elapsed_ms': (C.c_float, [_vp, _vp]),

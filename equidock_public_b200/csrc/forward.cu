@@ -49,6 +49,38 @@ Carve carve(const eqd_graph* g) {
 
 extern "C" size_t eqd_forward_workspace_bytes(const eqd_graph* g) { return g ? carve(g).total : 0; }
 
+// ---- training stash: the per-layer inputs the backward kernels recompute from -----------------------------------------
+namespace {
+struct Stash {
+  size_t h0, x, h, aggr, mu, total, x_stride, h_stride, a_stride, m_stride;
+};
+Stash stash_layout(const eqd_graph* g, int n_layers) {
+  Stash s;
+  const size_t N = (size_t)(g->n_nodes > 0 ? g->n_nodes : 0), L = (size_t)(n_layers > 0 ? n_layers : 0);
+  s.x_stride = al256(N * 3 * 8);
+  s.h_stride = al256(N * EQD_HID * 4);
+  s.a_stride = al256(N * EQD_HID * 4);
+  s.m_stride = al256(N * EQD_H0_PAD * 4);
+  size_t o = 0;
+  s.h0 = o; o += al256(N * EQD_H0_PAD * 4);
+  s.x = o; o += L * s.x_stride;          // x[l] = coordinates entering layer l (x[0] = input coordinates)
+  s.h = o; o += L * s.h_stride;          // h[l] = features entering layer l, l >= 1 (slot 0 unused: layer 0 reads h0)
+  s.aggr = o; o += L * s.a_stride;       // aggr[l] = mean edge message of layer l
+  s.mu = o; o += L * s.m_stride;         // mu[l] = attention output of layer l (row stride 72 for layer 0, else 64)
+  s.total = o;
+  return s;
+}
+}  // namespace
+
+extern "C" size_t eqd_forward_stash_bytes(const eqd_graph* g, int32_t n_layers) { return g ? stash_layout(g, n_layers).total : 0; }
+extern "C" int eqd_forward_stash_offsets(const eqd_graph* g, int32_t n_layers, size_t* out /*[9]*/) {
+  if (!g || !out) return EQD_ERR_BAD_ARG;
+  const Stash s = stash_layout(g, n_layers);
+  out[0] = s.h0; out[1] = s.x; out[2] = s.x_stride; out[3] = s.h; out[4] = s.h_stride; out[5] = s.aggr; out[6] = s.a_stride;
+  out[7] = s.mu; out[8] = s.m_stride;
+  return EQD_OK;
+}
+
 extern "C" int eqd_iegmn_forward(const eqd_graph* g, const eqd_layer_params* const* layers, int32_t n_layers,
                                  const eqd_head_params* hp, const eqd_forward_io* io, void* workspace,
                                  size_t workspace_bytes, void* stream) {
@@ -82,6 +114,16 @@ extern "C" int eqd_iegmn_forward(const eqd_graph* g, const eqd_layer_params* con
   double* ymean = io->ymean ? io->ymean : reinterpret_cast<double*>(w + c.ymean);
   double* cov = io->cov ? io->cov : reinterpret_cast<double*>(w + c.cov);
   const int N = g->n_nodes, B = g->n_pairs;
+  // training: every layer's inputs (h, x), mean edge message and attention output go to the caller's stash instead of the
+  // ping-pong buffers, so that the backward kernels can recompute each layer from them
+  unsigned char* sb = reinterpret_cast<unsigned char*>(io->train_stash);
+  Stash sl;
+  if (sb) {
+    sl = stash_layout(g, n_layers);
+    if (io->train_stash_bytes < sl.total || (reinterpret_cast<uintptr_t>(sb) & 255)) return EQD_ERR_WORKSPACE;
+    h0 = reinterpret_cast<float*>(sb + sl.h0);
+    x0 = reinterpret_cast<double*>(sb + sl.x);
+  }
 
   // rows the kernels never write but the tensor cores / TMA read: the tail of the last 8-node block and the 8 pad
   // blocks of each (K|V, split) plane, and the pad rows of x5 (they reach P.V as 0 x value: must be finite)
@@ -113,6 +155,14 @@ extern "C" int eqd_iegmn_forward(const eqd_graph* g, const eqd_layer_params* con
     const bool last = lpn == nullptr;
     float* h_out = last ? io->h_out : hbuf[li & 1];
     double* x_out = last ? io->x_out : xbuf[li & 1];
+    if (sb) {
+      if (!last) {
+        h_out = reinterpret_cast<float*>(sb + sl.h + (size_t)(li + 1) * sl.h_stride);
+        x_out = reinterpret_cast<double*>(sb + sl.x + (size_t)(li + 1) * sl.x_stride);
+      }
+      aggr = reinterpret_cast<float*>(sb + sl.aggr + (size_t)li * sl.a_stride);
+      mu = reinterpret_cast<float*>(sb + sl.mu + (size_t)li * sl.m_stride);
+    }
     stage_event(li, 0);
     rc = eqd_edge_stage(g, lp, pa, x_in, x0, aggr, x_out, io->status, stream);
     if (rc) return rc;

@@ -520,3 +520,395 @@ extern "C" int eqd_kabsch_apply(const eqd_graph* g, const double* cov, const dou
   EQD_CUDA_LAUNCH_CHECK();
   return EQD_OK;
 }
+
+// =====================================================================================================================
+// BACKWARD of the keypoint read-out and the Kabsch step (no code in the reference: what loss.backward(), train.py:154,
+// makes of rigid_docking_model.py:521-589, 657-665).  fp64 throughout; every reduction in a fixed order.  Restated in
+// oracle/backward_manual.py::kabsch_bwd / svd_rotation_backward / keypoints_bwd.
+// =====================================================================================================================
+namespace eqd {
+
+// One CTA per pair.  coords = T new_x + b (:665), b = ym_r - T ym_l (:589), T = U D V^T with D = diag(1,1,sign det A) a
+// constant (:586-587), A = (Y_r - ym_r)^T (Y_l - ym_l) (:567).  gA = U [ (skew(U^T gU)/E) S + S (skew(V^T gV)/E) ] V^T with
+// gU = gT V D, gV = gT^T U D, E_jk = S_k^2 - S_j^2 (torch's svd_backward; |E| >= 1e-2 is what the guard :574 enforces).
+__global__ void __launch_bounds__(128)
+kabsch_bwd_kernel(eqd_graph g, const double* __restrict__ cov, const double* __restrict__ ymean,
+                  const double* __restrict__ keypts, const float* __restrict__ x_lig_in, const float* __restrict__ dcoors,
+                  const double* __restrict__ dY_direct, const float* __restrict__ drot, const float* __restrict__ dtrans,
+                  double* __restrict__ dY) {
+  const int b = blockIdx.x, tid = threadIdx.x, B = g.n_pairs;
+  __shared__ double red[128][12];
+  __shared__ double dA[9], dyml[3], dymr[3];
+  const int i0 = g.seg_ptr[b], i1 = g.seg_ptr[b + 1];
+  double acc[12];
+#pragma unroll
+  for (int q = 0; q < 12; ++q) acc[q] = 0.0;
+  if (dcoors) {
+    for (int i = i0 + tid; i < i1; i += 128) {
+      const double gx = dcoors[(long)i * 3], gy = dcoors[(long)i * 3 + 1], gz = dcoors[(long)i * 3 + 2];
+      const double px = x_lig_in[(long)i * 3], py = x_lig_in[(long)i * 3 + 1], pz = x_lig_in[(long)i * 3 + 2];
+      acc[0] += gx * px; acc[1] += gx * py; acc[2] += gx * pz;
+      acc[3] += gy * px; acc[4] += gy * py; acc[5] += gy * pz;
+      acc[6] += gz * px; acc[7] += gz * py; acc[8] += gz * pz;
+      acc[9] += gx; acc[10] += gy; acc[11] += gz;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 12; ++q) red[tid][q] = acc[q];
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) {
+    if (tid < s)
+#pragma unroll
+      for (int q = 0; q < 12; ++q) red[tid][q] += red[tid + s][q];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    double gT[9], gb[3], A[9], U[9], S[3], V[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) gT[q] = red[0][q] + (drot ? (double)drot[(long)b * 9 + q] : 0.0);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) gb[q] = red[0][9 + q] + (dtrans ? (double)dtrans[(long)b * 3 + q] : 0.0);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) A[q] = cov[(long)b * 9 + q];
+    svd3(A, U, S, V);
+    const double det = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) +
+                       A[2] * (A[3] * A[7] - A[4] * A[6]);
+    const double sg = det > 0.0 ? 1.0 : (det < 0.0 ? -1.0 : 0.0);
+    const double Dg[3] = {1.0, 1.0, sg};
+    const double* ml = ymean + (long)b * 3;
+    const double* mr = ymean + (long)(B + b) * 3;
+    double T[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        T[r * 3 + c] = U[r * 3] * V[c * 3] + U[r * 3 + 1] * V[c * 3 + 1] + sg * U[r * 3 + 2] * V[c * 3 + 2];
+    // b = ym_r - T ym_l
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      dymr[r] = gb[r];
+      dyml[r] = -(T[0 * 3 + r] * gb[0] + T[1 * 3 + r] * gb[1] + T[2 * 3 + r] * gb[2]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gT[r * 3 + c] -= gb[r] * ml[c];
+    }
+    // gU = gT V D ; gV = gT^T U D
+    double gU[9], gV[9], P[9], Q[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        gU[r * 3 + c] = (gT[r * 3] * V[0 * 3 + c] + gT[r * 3 + 1] * V[1 * 3 + c] + gT[r * 3 + 2] * V[2 * 3 + c]) * Dg[c];
+        gV[r * 3 + c] = (gT[0 * 3 + r] * U[0 * 3 + c] + gT[1 * 3 + r] * U[1 * 3 + c] + gT[2 * 3 + r] * U[2 * 3 + c]) * Dg[c];
+      }
+    // P = U^T gU, Q = V^T gV
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        P[r * 3 + c] = U[0 * 3 + r] * gU[0 * 3 + c] + U[1 * 3 + r] * gU[1 * 3 + c] + U[2 * 3 + r] * gU[2 * 3 + c];
+        Q[r * 3 + c] = V[0 * 3 + r] * gV[0 * 3 + c] + V[1 * 3 + r] * gV[1 * 3 + c] + V[2 * 3 + r] * gV[2 * 3 + c];
+      }
+    double In[9];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (j == k) { In[j * 3 + k] = 0.0; continue; }
+        const double E = S[k] * S[k] - S[j] * S[j];
+        In[j * 3 + k] = ((P[j * 3 + k] - P[k * 3 + j]) / E) * S[k] + S[j] * ((Q[j * 3 + k] - Q[k * 3 + j]) / E);
+      }
+    // gA = U In V^T
+    double UI[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) UI[r * 3 + c] = U[r * 3] * In[0 * 3 + c] + U[r * 3 + 1] * In[1 * 3 + c] + U[r * 3 + 2] * In[2 * 3 + c];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dA[r * 3 + c] = UI[r * 3] * V[c * 3] + UI[r * 3 + 1] * V[c * 3 + 1] + UI[r * 3 + 2] * V[c * 3 + 2];
+  }
+  __syncthreads();
+  // dYc_r = Yc_l dA^T, dYc_l = Yc_r dA; un-centre: dY = dYc - mean_k(dYc) + dym / K
+  __shared__ double dyc[2][EQD_HEADS][3];
+  const double* ml = ymean + (long)b * 3;
+  const double* mr = ymean + (long)(B + b) * 3;
+  const double* yl = keypts + (long)b * EQD_HEADS * 3;
+  const double* yr = keypts + (long)(B + b) * EQD_HEADS * 3;
+  if (tid < EQD_HEADS) {
+    const int k = tid;
+    const double cl[3] = {yl[k * 3] - ml[0], yl[k * 3 + 1] - ml[1], yl[k * 3 + 2] - ml[2]};
+    const double cr[3] = {yr[k * 3] - mr[0], yr[k * 3 + 1] - mr[1], yr[k * 3 + 2] - mr[2]};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      dyc[1][k][c] = cl[0] * dA[c * 3 + 0] + cl[1] * dA[c * 3 + 1] + cl[2] * dA[c * 3 + 2];   // (Yc_l dA^T)[k][c]
+      dyc[0][k][c] = cr[0] * dA[0 * 3 + c] + cr[1] * dA[1 * 3 + c] + cr[2] * dA[2 * 3 + c];   // (Yc_r dA)[k][c]
+    }
+  }
+  __syncthreads();
+  __shared__ double mean_d[2][3];
+  if (tid < 6) {
+    const int side = tid / 3, c = tid % 3;
+    double t = 0.0;
+    for (int k = 0; k < EQD_HEADS; ++k) t += dyc[side][k][c];
+    mean_d[side][c] = t / (double)EQD_HEADS;
+  }
+  __syncthreads();
+  for (int o = tid; o < 2 * EQD_HEADS * 3; o += 128) {
+    const int side = o / (EQD_HEADS * 3), rem = o - side * EQD_HEADS * 3, k = rem / 3, c = rem - k * 3;
+    const long gi = ((long)(side == 0 ? b : B + b) * EQD_HEADS + k) * 3 + c;
+    double v = dyc[side][k][c] - mean_d[side][c] + (side == 0 ? dyml[c] : dymr[c]) / (double)EQD_HEADS;
+    if (dY_direct) v += dY_direct[gi];
+    dY[gi] = v;
+  }
+}
+
+// logits[n][k] = h_n . u[seg(n)][k]   (warp per node, lanes over heads)
+__global__ void kp_logits_kernel(eqd_graph g, const int* __restrict__ node_seg, const float* __restrict__ h,
+                                 const double* __restrict__ u, double* __restrict__ logits) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= g.n_nodes) return;
+  const int s = node_seg[n];
+  const float* hr = h + (long)n * EQD_HID;
+  for (int k = lane; k < EQD_HEADS; k += 32) {
+    const double* uk = u + ((long)s * EQD_HEADS + k) * 64;
+    double t = 0.0;
+#pragma unroll 8
+    for (int d = 0; d < 64; ++d) t = fma((double)hr[d], uk[d], t);
+    logits[(long)n * EQD_HEADS + k] = t;
+  }
+}
+
+// per (segment, head): softmax statistics over the segment's nodes and c_k = dY_k . Y_k.  stats[s][k] = {m, 1/l, c}
+__global__ void kp_stats_kernel(eqd_graph g, const double* __restrict__ logits, const double* __restrict__ keypts,
+                                const double* __restrict__ dY, double* __restrict__ stats) {
+  const int s = blockIdx.x, k = threadIdx.x;
+  if (k >= EQD_HEADS) return;
+  const int i0 = g.seg_ptr[s], i1 = g.seg_ptr[s + 1];
+  double m = -INFINITY;
+  for (int i = i0; i < i1; ++i) m = fmax(m, logits[(long)i * EQD_HEADS + k]);
+  double l = 0.0;
+  for (int i = i0; i < i1; ++i) l += exp(logits[(long)i * EQD_HEADS + k] - m);
+  const double* y = keypts + ((long)s * EQD_HEADS + k) * 3;
+  const double* d = dY + ((long)s * EQD_HEADS + k) * 3;
+  double* o = stats + ((long)s * EQD_HEADS + k) * 3;
+  o[0] = m;
+  o[1] = l > 0.0 ? 1.0 / l : 0.0;
+  o[2] = d[0] * y[0] + d[1] * y[1] + d[2] * y[2];
+}
+
+// warp per node n: att_k = exp(logit - m_k) / l_k; dlog_k = att_k (dY_k . z_n - c_k) (overwrites logits[n][k]);
+// dz_n = sum_k att_k dY_k -> dx[n];  dh[n][d] = sum_k dlog_k u_k[d]
+__global__ void kp_node_bwd_kernel(eqd_graph g, const int* __restrict__ node_seg, const double* __restrict__ x,
+                                   const double* __restrict__ u, const double* __restrict__ dY,
+                                   const double* __restrict__ stats, double* __restrict__ logits,
+                                   double* __restrict__ dx, float* __restrict__ dh) {
+  __shared__ double dl[8][EQD_HEADS + 2];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + w;
+  if (n < g.n_nodes) {
+    const int s = node_seg[n];
+    const double zx = x[(long)n * 3], zy = x[(long)n * 3 + 1], zz = x[(long)n * 3 + 2];
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    for (int k = lane; k < EQD_HEADS; k += 32) {
+      const double* st = stats + ((long)s * EQD_HEADS + k) * 3;
+      const double* d = dY + ((long)s * EQD_HEADS + k) * 3;
+      const double att = exp(logits[(long)n * EQD_HEADS + k] - st[0]) * st[1];
+      const double dlog = att * (d[0] * zx + d[1] * zy + d[2] * zz - st[2]);
+      logits[(long)n * EQD_HEADS + k] = dlog;
+      dl[w][k] = dlog;
+      ax += att * d[0]; ay += att * d[1]; az += att * d[2];
+    }
+    ax = warp_sum_d(ax); ay = warp_sum_d(ay); az = warp_sum_d(az);
+    if (lane == 0) { dx[(long)n * 3] = ax; dx[(long)n * 3 + 1] = ay; dx[(long)n * 3 + 2] = az; }
+    __syncwarp();
+    double a0 = 0.0, a1 = 0.0;
+    for (int k = 0; k < EQD_HEADS; ++k) {
+      const double* uk = u + ((long)s * EQD_HEADS + k) * 64;
+      a0 = fma(dl[w][k], uk[lane], a0);
+      a1 = fma(dl[w][k], uk[lane + 32], a1);
+    }
+    dh[(long)n * EQD_HID + lane] = (float)a0;
+    dh[(long)n * EQD_HID + lane + 32] = (float)a1;
+  }
+}
+
+// du[s][k][d] = sum_{n in seg s} dlog[n][k] h[n][d]   (CTA per segment, fixed order over n)
+__global__ void __launch_bounds__(256) kp_du_kernel(eqd_graph g, const double* __restrict__ dlog, const float* __restrict__ h,
+                                                    double* __restrict__ du) {
+  const int s = blockIdx.x, i0 = g.seg_ptr[s], i1 = g.seg_ptr[s + 1];
+  for (int o = threadIdx.x; o < EQD_HEADS * 64; o += 256) {
+    const int k = o >> 6, d = o & 63;
+    double t = 0.0;
+    for (int i = i0; i < i1; ++i) t = fma(dlog[(long)i * EQD_HEADS + k], (double)h[(long)i * EQD_HID + d], t);
+    du[(long)s * EQD_HEADS * 64 + o] = t;
+  }
+}
+
+// CTA per head k: over all segments s (fixed order): r = W_Q,k qbar_partner(s), a = W_K,k du_{s,k} / 8,
+// dW_K,k[e][d] += r[e] du[d] / 8, dW_Q,k[e][d'] += a[e] qbar_partner[d'].  a is kept for the dqbar pass.
+__global__ void __launch_bounds__(256)
+head_weight_bwd_kernel(int n_pairs, eqd_head_params hp, const double* __restrict__ qbar, const double* __restrict__ du,
+                       double* __restrict__ a_out /*[2B][50][64]*/, float* __restrict__ g_wkey, float* __restrict__ g_wquery) {
+  __shared__ float wq[64][65], wk[64][65];
+  __shared__ double r[64], a[64], qb[64], dv[64];
+  const int k = blockIdx.x, tid = threadIdx.x, nseg = 2 * n_pairs;
+  for (int i = tid; i < 64 * 64; i += 256) {
+    wq[i >> 6][i & 63] = hp.w_query[(long)k * 4096 + i];
+    wk[i >> 6][i & 63] = hp.w_key[(long)k * 4096 + i];
+  }
+  double gk[16], gq[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) gk[q] = gq[q] = 0.0;
+  const int e0 = (tid >> 6) * 16, d = tid & 63;      // this thread owns (e0 .. e0+15, d)
+  for (int s = 0; s < nseg; ++s) {
+    const int ps = s < n_pairs ? s + n_pairs : s - n_pairs;
+    __syncthreads();
+    if (tid < 64) {
+      qb[tid] = qbar[(long)ps * 64 + tid];
+      dv[tid] = du[((long)s * EQD_HEADS + k) * 64 + tid];
+    }
+    __syncthreads();
+    if (tid < 64) {
+      double t = 0.0;
+      for (int dd = 0; dd < 64; ++dd) t = fma((double)wq[tid][dd], qb[dd], t);
+      r[tid] = t;
+    } else if (tid < 128) {
+      const int e = tid - 64;
+      double t = 0.0;
+      for (int dd = 0; dd < 64; ++dd) t = fma((double)wk[e][dd], dv[dd], t);
+      a[e] = t * 0.125;
+      a_out[((long)s * EQD_HEADS + k) * 64 + e] = t * 0.125;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      gk[q] = fma(r[e0 + q] * 0.125, dv[d], gk[q]);
+      gq[q] = fma(a[e0 + q], qb[d], gq[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    g_wkey[((long)k * 64 + e0 + q) * 64 + d] += (float)gk[q];
+    g_wquery[((long)k * 64 + e0 + q) * 64 + d] += (float)gq[q];
+  }
+}
+
+// dqbar[p][d'] = sum_k sum_e W_Q,k[e][d'] a[partner(p)][k][e]      (CTA per segment p, 64 threads)
+__global__ void head_dqbar_kernel(int n_pairs, eqd_head_params hp, const double* __restrict__ a, double* __restrict__ dqbar) {
+  const int p = blockIdx.x, dq = threadIdx.x;
+  const int s = p < n_pairs ? p + n_pairs : p - n_pairs;     // the segment whose keypoints used qbar_p
+  double t = 0.0;
+  for (int k = 0; k < EQD_HEADS; ++k) {
+    const double* ak = a + ((long)s * EQD_HEADS + k) * 64;
+    const float* w = hp.w_query + (long)k * 4096;
+    for (int e = 0; e < 64; ++e) t = fma((double)w[e * 64 + dq], ak[e], t);
+  }
+  dqbar[(long)p * 64 + dq] = t;
+}
+
+// warp per node: pre = W_m h + b_m; dpre = dqbar[seg] / n_seg * lrelu'(pre) -> dpre_out (D operand of dW_m);
+// dh[n] += W_m^T dpre
+__global__ void head_mean_bwd_kernel(eqd_graph g, eqd_head_params hp, const int* __restrict__ node_seg,
+                                     const float* __restrict__ h, const double* __restrict__ dqbar,
+                                     float* __restrict__ dpre_out, float* __restrict__ dh) {
+  __shared__ float hs[8][64], dp[8][64];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + w;
+  if (n >= g.n_nodes) return;
+  const int s = node_seg[n];
+  const float inv_n = 1.f / (float)(g.seg_ptr[s + 1] - g.seg_ptr[s]);
+  hs[w][lane] = h[(long)n * 64 + lane];
+  hs[w][lane + 32] = h[(long)n * 64 + lane + 32];
+  __syncwarp();
+  float p0 = hp.b_mean[lane], p1 = hp.b_mean[lane + 32];
+  for (int d = 0; d < 64; ++d) {       // w_mean is k-major [in d][out c]
+    p0 = fmaf(hs[w][d], hp.w_mean[d * 64 + lane], p0);
+    p1 = fmaf(hs[w][d], hp.w_mean[d * 64 + lane + 32], p1);
+  }
+  const float g0 = (float)dqbar[(long)s * 64 + lane] * inv_n * (p0 > 0.f ? 1.f : hp.leaky_slope);
+  const float g1 = (float)dqbar[(long)s * 64 + lane + 32] * inv_n * (p1 > 0.f ? 1.f : hp.leaky_slope);
+  dpre_out[(long)n * 64 + lane] = g0;
+  dpre_out[(long)n * 64 + lane + 32] = g1;
+  dp[w][lane] = g0;
+  dp[w][lane + 32] = g1;
+  __syncwarp();
+  float a0 = 0.f, a1 = 0.f;
+  for (int c = 0; c < 64; ++c) {       // dh[d] = sum_c W_m[c][d] dpre[c] = sum_c w_mean[d][c] dpre[c]
+    a0 = fmaf(hp.w_mean[lane * 64 + c], dp[w][c], a0);
+    a1 = fmaf(hp.w_mean[(lane + 32) * 64 + c], dp[w][c], a1);
+  }
+  dh[(long)n * 64 + lane] += a0;
+  dh[(long)n * 64 + lane + 32] += a1;
+}
+
+__global__ void node_seg_kernel(eqd_graph g, int* __restrict__ node_seg) {
+  const int s = blockIdx.x;
+  for (int i = g.seg_ptr[s] + threadIdx.x; i < g.seg_ptr[s + 1]; i += blockDim.x) node_seg[i] = s;
+}
+
+}  // namespace eqd
+
+extern "C" size_t eqd_bwd_head_workspace_bytes(int32_t n_nodes, int32_t n_node_tiles, int32_t n_pairs) {
+  const size_t N = n_nodes > 0 ? n_nodes : 1, B = n_pairs > 0 ? n_pairs : 1;
+  return eqd_workspace_bytes(n_nodes, n_node_tiles, n_pairs)      // forward intermediates (qbar, u) are recomputed
+         + eqd_align256(2 * B * EQD_HEADS * 3 * 8) * 2 + eqd_align256(B * 9 * 8) + eqd_align256(2 * B * 3 * 8)   // keypts, dY, cov, ymean
+         + eqd_align256(N * 4) + eqd_align256(N * EQD_HEADS * 8) + eqd_align256(2 * B * EQD_HEADS * 3 * 8)       // node_seg, logits, stats
+         + eqd_align256(2 * B * EQD_HEADS * 64 * 8) * 2 + eqd_align256(2 * B * 64 * 8);                           // du, a, dqbar
+}
+
+// Backward of eqd_keypoints + eqd_kabsch_apply.  Inputs: last-layer h (fp32) / x (fp64), `cov` as left by the forward
+// (incl. any guard perturbation), the upstream gradients dcoors [N_l][3] (fp32, may be NULL), dkeypts [2B][50][3] (fp64,
+// may be NULL), drot [B][9], dtrans [B][3] (fp32, may be NULL).  Outputs: dh [n][64] (fp32, overwritten), dx [n][3]
+// (fp64, overwritten), dpre [n][64] (the D operand of d mlp_h_mean_ROT.0.weight = dpre^T h, reduced by the caller with
+// eqd_tn_gemm), and the head weight gradients accumulated into g_wkey / g_wquery (state_dict layouts [3200][64]).
+extern "C" int eqd_bwd_head(const eqd_graph* g, const eqd_head_params* hp, const float* h, const double* x,
+                            const double* cov, const float* x_lig_in, const float* dcoors, const double* dkeypts,
+                            const float* drot, const float* dtrans, void* workspace, size_t workspace_bytes, float* dh,
+                            double* dx, float* dpre, float* g_wkey, float* g_wquery, void* stream) {
+  if (!g || !hp || !h || !x || !cov || !x_lig_in || !workspace || !dh || !dx || !dpre || !g_wkey || !g_wquery)
+    return EQD_ERR_BAD_ARG;
+  if (workspace_bytes < eqd_bwd_head_workspace_bytes(g->n_nodes, g->n_node_tiles, g->n_pairs)) return EQD_ERR_WORKSPACE;
+  if (g->n_pairs <= 0) return EQD_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t N = g->n_nodes, B = g->n_pairs;
+  unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { unsigned char* p = w + o; o += eqd_align256(bytes); return p; };
+  const size_t fwd_bytes = eqd_workspace_bytes(g->n_nodes, g->n_node_tiles, g->n_pairs);
+  unsigned char* fwd_ws = take(fwd_bytes);
+  double* keypts = reinterpret_cast<double*>(take(2 * B * EQD_HEADS * 3 * 8));
+  double* dY = reinterpret_cast<double*>(take(2 * B * EQD_HEADS * 3 * 8));
+  double* cov_scratch = reinterpret_cast<double*>(take(B * 9 * 8));
+  double* ymean = reinterpret_cast<double*>(take(2 * B * 3 * 8));
+  int* node_seg = reinterpret_cast<int*>(take(N * 4));
+  double* logits = reinterpret_cast<double*>(take(N * EQD_HEADS * 8));
+  double* stats = reinterpret_cast<double*>(take(2 * B * EQD_HEADS * 3 * 8));
+  double* du = reinterpret_cast<double*>(take(2 * B * EQD_HEADS * 64 * 8));
+  double* a = reinterpret_cast<double*>(take(2 * B * EQD_HEADS * 64 * 8));
+  double* dqbar = reinterpret_cast<double*>(take(2 * B * 64 * 8));
+  // recompute qbar, u, keypoints and their means (cov_scratch is discarded: the caller's cov may carry the guard's noise)
+  int rc = eqd_keypoints(g, hp, h, x, fwd_ws, fwd_bytes, keypts, ymean, cov_scratch, stream);
+  if (rc) return rc;
+  const double* qbar = reinterpret_cast<const double*>(fwd_ws + ws_part_bytes(g->n_node_tiles) + ws_tile_ptr_bytes(g->n_pairs));
+  const double* u = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(qbar) + ws_qbar_bytes(g->n_pairs));
+  eqd::kabsch_bwd_kernel<<<g->n_pairs, 128, 0, st>>>(*g, cov, ymean, keypts, x_lig_in, dcoors, dkeypts, drot, dtrans, dY);
+  EQD_CUDA_LAUNCH_CHECK();
+  eqd::node_seg_kernel<<<2 * g->n_pairs, 128, 0, st>>>(*g, node_seg);
+  EQD_CUDA_LAUNCH_CHECK();
+  eqd::kp_logits_kernel<<<(unsigned)((N * 32 + 255) / 256), 256, 0, st>>>(*g, node_seg, h, u, logits);
+  EQD_CUDA_LAUNCH_CHECK();
+  eqd::kp_stats_kernel<<<2 * g->n_pairs, 64, 0, st>>>(*g, logits, keypts, dY, stats);
+  EQD_CUDA_LAUNCH_CHECK();
+  eqd::kp_node_bwd_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(*g, node_seg, x, u, dY, stats, logits, dx, dh);
+  EQD_CUDA_LAUNCH_CHECK();
+  eqd::kp_du_kernel<<<2 * g->n_pairs, 256, 0, st>>>(*g, logits, h, du);
+  EQD_CUDA_LAUNCH_CHECK();
+  eqd::head_weight_bwd_kernel<<<EQD_HEADS, 256, 0, st>>>(g->n_pairs, *hp, qbar, du, a, g_wkey, g_wquery);
+  EQD_CUDA_LAUNCH_CHECK();
+  eqd::head_dqbar_kernel<<<2 * g->n_pairs, 64, 0, st>>>(g->n_pairs, *hp, a, dqbar);
+  EQD_CUDA_LAUNCH_CHECK();
+  eqd::head_mean_bwd_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(*g, *hp, node_seg, h, dqbar, dpre, dh);
+  EQD_CUDA_LAUNCH_CHECK();
+  return EQD_OK;
+}

@@ -1,0 +1,344 @@
+// Training losses of the reference on the device, one CTA per protein pair, with their gradients:
+//   * per-pair MSE of the predicted ligand C-alpha coordinates (nn.MSELoss, src/train.py:114)
+//   * body-intersection loss (src/train.py:41-49, 131-133): two n x m Gaussian log-sum reductions
+//   * pocket OT loss (src/train.py:125-129, src/utils/ot_utils.py:5-29): cost = |P_l - Y_l|^2 + |P_r - Y_r|^2 between the
+//     N_pocket pocket points and the 50 keypoints, EXACT earth mover's distance with uniform marginals.  The reference calls
+//     POT's network simplex on the CPU (ot.emd, a D2H/H2D round trip per pair); here the transport LP is solved on the SM
+//     by successive shortest augmenting paths with node potentials (primal-dual; Dijkstra on the dense bipartite residual
+//     graph, integer flows in units of 1/(N_pocket * 50)), which terminates at the LP optimum -- the unique optimal VALUE any
+//     exact solver returns.  The plan is a constant for the gradient (ot_utils.py:27): dY = 2 sum_i T_ik (Y_k - P_i).
+// Everything in fp64; all reductions in a fixed order.  Restated in oracle/loss_oracle.py.
+#include "common.cuh"
+
+namespace eqd {
+
+#define LOSS_THREADS 128
+#define OT_MAX_POCKET 1024
+
+__device__ __forceinline__ double block_sum_d(double v, double* sh /*[LOSS_THREADS]*/) {
+  __syncthreads();
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = LOSS_THREADS / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// parts[b] = {mse, intersection}; dcoors[i] = d (mse/B + w_int * inter/B) / d pred_i
+__global__ void __launch_bounds__(LOSS_THREADS)
+loss_mse_intersection_kernel(eqd_graph g, const float* __restrict__ pred, const float* __restrict__ tgt_lig,
+                             const float* __restrict__ rec, double sigma, double surface_ct, double w_int,
+                             double* __restrict__ wrec /*[N_r] scratch*/, double* __restrict__ parts,
+                             float* __restrict__ dcoors) {
+  __shared__ double sh[LOSS_THREADS];
+  const int b = blockIdx.x, B = g.n_pairs, tid = threadIdx.x;
+  const int l0 = g.seg_ptr[b], l1 = g.seg_ptr[b + 1];
+  const int r0 = g.seg_ptr[B + b] - g.n_lig_nodes, r1 = g.seg_ptr[B + b + 1] - g.n_lig_nodes;   // receptor-local ids
+  const int nl = l1 - l0, nr = r1 - r0;
+  const double invB = 1.0 / (double)B;
+  // pass B first: per receptor point, S_i = 1e-3 + sum_j exp(-|y_i - l_j|^2 / sigma) -> active weight
+  double t2 = 0.0;
+  for (int i = r0 + tid; i < r1; i += LOSS_THREADS) {
+    const double yx = rec[(long)i * 3], yy = rec[(long)i * 3 + 1], yz = rec[(long)i * 3 + 2];
+    double S = 1e-3;
+    for (int j = l0; j < l1; ++j) {
+      const double dx = yx - pred[(long)j * 3], dy = yy - pred[(long)j * 3 + 1], dz = yz - pred[(long)j * 3 + 2];
+      S += exp(-(dx * dx + dy * dy + dz * dz) / sigma);
+    }
+    const double val = surface_ct + sigma * log(S);       // ct - G_lig(y_i)
+    const bool act = val > 0.0;
+    t2 += act ? val : 0.0;
+    wrec[i] = act ? 1.0 / ((double)nr * S) : 0.0;
+  }
+  const double term2 = block_sum_d(t2, sh) / (double)(nr > 0 ? nr : 1);
+  __threadfence_block();
+  __syncthreads();
+  double t1 = 0.0, tm = 0.0;
+  for (int j = l0 + tid; j < l1; j += LOSS_THREADS) {
+    const double px = pred[(long)j * 3], py = pred[(long)j * 3 + 1], pz = pred[(long)j * 3 + 2];
+    double S = 1e-3, vx = 0.0, vy = 0.0, vz = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+    for (int i = r0; i < r1; ++i) {
+      const double dx = px - rec[(long)i * 3], dy = py - rec[(long)i * 3 + 1], dz = pz - rec[(long)i * 3 + 2];
+      const double e = exp(-(dx * dx + dy * dy + dz * dz) / sigma);
+      S += e;
+      vx += e * dx; vy += e * dy; vz += e * dz;
+      const double w = wrec[i] * e;                         // term 2: d/d l_j = 2 e_ij (y_i - l_j) / (n_r S_i) = -2 w (l_j - y_i)
+      gx -= w * dx; gy -= w * dy; gz -= w * dz;
+    }
+    const double val = surface_ct + sigma * log(S);         // ct - G_rec(l_j)
+    const bool act = val > 0.0;
+    t1 += act ? val : 0.0;
+    const double c1 = act ? -2.0 / ((double)nl * S) : 0.0;  // d(ct - G_rec)/d l_j = -2 sum_i e_i (l_j - r_i) / S
+    const double ex = px - tgt_lig[(long)j * 3], ey = py - tgt_lig[(long)j * 3 + 1], ez = pz - tgt_lig[(long)j * 3 + 2];
+    tm += ex * ex + ey * ey + ez * ez;
+    const double cm = 2.0 / (3.0 * (double)nl);
+    dcoors[(long)j * 3 + 0] = (float)(invB * (cm * ex + w_int * (c1 * vx + 2.0 * gx)));
+    dcoors[(long)j * 3 + 1] = (float)(invB * (cm * ey + w_int * (c1 * vy + 2.0 * gy)));
+    dcoors[(long)j * 3 + 2] = (float)(invB * (cm * ez + w_int * (c1 * vz + 2.0 * gz)));
+  }
+  const double term1 = block_sum_d(t1, sh) / (double)(nl > 0 ? nl : 1);
+  const double mse = block_sum_d(tm, sh) / (3.0 * (double)(nl > 0 ? nl : 1));
+  if (tid == 0) {
+    parts[(long)b * 4 + 0] = mse;
+    parts[(long)b * 4 + 2] = term1 + term2;
+  }
+}
+
+struct OtSmem {
+  double P[OT_MAX_POCKET * 6];      // pocket points: ligand xyz, receptor xyz
+  double Y[EQD_HEADS * 6];          // keypoints: ligand xyz, receptor xyz
+  double u[OT_MAX_POCKET], ds[OT_MAX_POCKET];
+  double v[EQD_HEADS], dk[EQD_HEADS];
+  int excess[OT_MAX_POCKET], par_s[OT_MAX_POCKET];
+  int deficit[EQD_HEADS], par_k[EQD_HEADS];
+  unsigned char vis_s[OT_MAX_POCKET], vis_k[EQD_HEADS + 14];
+  double red_v[LOSS_THREADS];
+  int red_i[LOSS_THREADS];
+  int ctl[4];
+};
+
+__device__ __forceinline__ double ot_cost(const OtSmem& s, int i, int k) {
+  const double* p = s.P + i * 6;
+  const double* y = s.Y + k * 6;
+  double c = 0.0;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const double d = p[q] - y[q];
+    c = fma(d, d, c);
+  }
+  return c;
+}
+
+// One CTA per pair.  flow[pocket_ptr[b] .. ][50] (int32, global) = transported mass in units of 1/(n*50).
+__global__ void __launch_bounds__(LOSS_THREADS)
+ot_emd_kernel(int n_pairs, const int* __restrict__ pocket_ptr, const float* __restrict__ pocket_lig,
+              const float* __restrict__ pocket_rec, const double* __restrict__ keypts, double w_ot,
+              int* __restrict__ flow, double* __restrict__ parts, double* __restrict__ dkeypts, int* __restrict__ err) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  OtSmem& s = *reinterpret_cast<OtSmem*>(smem_raw);
+  const int b = blockIdx.x, tid = threadIdx.x, B = n_pairs;
+  const int p0 = pocket_ptr[b], n = pocket_ptr[b + 1] - p0;
+  constexpr int M = EQD_HEADS;
+  if (n <= 0 || n > OT_MAX_POCKET) {
+    if (tid == 0) {
+      parts[(long)b * 4 + 1] = 0.0;
+      if (n > OT_MAX_POCKET) atomicOr(err, 1);
+    }
+    for (int o = tid; o < 2 * M * 3; o += LOSS_THREADS) {
+      const int side = o / (M * 3), rem = o - side * M * 3;
+      dkeypts[((long)(side == 0 ? b : B + b) * M) * 3 + rem] = 0.0;
+    }
+    return;
+  }
+  for (int o = tid; o < n * 3; o += LOSS_THREADS) {
+    const int i = o / 3, c = o - i * 3;
+    s.P[i * 6 + c] = (double)pocket_lig[(long)(p0 + i) * 3 + c];
+    s.P[i * 6 + 3 + c] = (double)pocket_rec[(long)(p0 + i) * 3 + c];
+  }
+  for (int o = tid; o < M * 3; o += LOSS_THREADS) {
+    const int k = o / 3, c = o - k * 3;
+    s.Y[k * 6 + c] = keypts[((long)b * M + k) * 3 + c];
+    s.Y[k * 6 + 3 + c] = keypts[((long)(B + b) * M + k) * 3 + c];
+  }
+  int* x = flow + (long)p0 * M;
+  for (int o = tid; o < n * M; o += LOSS_THREADS) x[o] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += LOSS_THREADS) {     // u_i = min_k C_ik, v = 0: all reduced costs >= 0
+    double mn = INFINITY;
+    for (int k = 0; k < M; ++k) mn = fmin(mn, ot_cost(s, i, k));
+    s.u[i] = mn;
+    s.excess[i] = M;
+  }
+  if (tid < M) { s.v[tid] = 0.0; s.deficit[tid] = n; }
+  if (tid == 0) s.ctl[0] = n * M;                    // mass still to ship
+  __syncthreads();
+  const long max_aug = 64L * (n + M) + 1024;
+  for (long it = 0; it < max_aug && s.ctl[0] > 0; ++it) {
+    // ---- multi-source Dijkstra on reduced costs; all sources with excess start at distance 0 and are settled at once ----
+    for (int i = tid; i < n; i += LOSS_THREADS) {
+      const bool ex = s.excess[i] > 0;
+      s.ds[i] = ex ? 0.0 : INFINITY;
+      s.vis_s[i] = ex ? 1 : 0;
+      s.par_s[i] = -1;
+    }
+    if (tid < M) { s.vis_k[tid] = 0; }
+    __syncthreads();
+    if (tid < M) {                                   // dk[k] = min over excess sources of rc_ik (ties: lowest i)
+      const int k = tid;
+      double best = INFINITY;
+      int bi = -1;
+      for (int i = 0; i < n; ++i)
+        if (s.excess[i] > 0) {
+          const double rc = fmax(ot_cost(s, i, k) - s.u[i] - s.v[k], 0.0);
+          if (rc < best) { best = rc; bi = i; }
+        }
+      s.dk[k] = best;
+      s.par_k[k] = bi;
+    }
+    __syncthreads();
+    int target = -1;
+    double D = 0.0;
+    for (int guard = 0; guard < n + M + 2; ++guard) {
+      // argmin over unvisited nodes (sinks first on ties, then lowest index: deterministic)
+      double bv = INFINITY;
+      int bidx = -1;                                 // sink k -> k ; source i -> M + i
+      if (tid < M && !s.vis_k[tid]) { bv = s.dk[tid]; bidx = tid; }
+      for (int i = tid; i < n; i += LOSS_THREADS)
+        if (!s.vis_s[i] && s.ds[i] < bv) { bv = s.ds[i]; bidx = M + i; }
+      s.red_v[tid] = bv;
+      s.red_i[tid] = bidx;
+      __syncthreads();
+      for (int st = LOSS_THREADS / 2; st > 0; st >>= 1) {
+        if (tid < st) {
+          const double ov = s.red_v[tid + st];
+          const int oi = s.red_i[tid + st];
+          if (oi >= 0 && (s.red_i[tid] < 0 || ov < s.red_v[tid] || (ov == s.red_v[tid] && oi < s.red_i[tid]))) {
+            s.red_v[tid] = ov;
+            s.red_i[tid] = oi;
+          }
+        }
+        __syncthreads();
+      }
+      const int node = s.red_i[0];
+      const double dist = s.red_v[0];
+      __syncthreads();
+      if (node < 0 || !(dist < INFINITY)) break;     // no augmenting path (cannot happen while mass remains)
+      if (node < M) {                                // a sink is settled
+        const int k = node;
+        if (s.deficit[k] > 0) { target = k; D = dist; break; }
+        if (tid == 0) s.vis_k[k] = 1;
+        for (int i = tid; i < n; i += LOSS_THREADS)  // backward arcs k -> i carry reduced cost 0 (complementary slackness)
+          if (!s.vis_s[i] && x[(long)i * M + k] > 0 && dist < s.ds[i]) { s.ds[i] = dist; s.par_s[i] = k; }
+      } else {                                       // a source is settled: relax its forward arcs
+        const int i = node - M;
+        if (tid == 0) s.vis_s[i] = 1;
+        if (tid < M && !s.vis_k[tid]) {
+          const double nd = dist + fmax(ot_cost(s, i, tid) - s.u[i] - s.v[tid], 0.0);
+          if (nd < s.dk[tid]) { s.dk[tid] = nd; s.par_k[tid] = i; }
+        }
+      }
+      __syncthreads();
+    }
+    if (target < 0) { if (tid == 0) atomicOr(err, 2); break; }
+    // ---- potentials: u_i -= min(ds_i, D), v_k += min(dk_k, D) ----
+    for (int i = tid; i < n; i += LOSS_THREADS) s.u[i] -= fmin(s.ds[i], D);
+    if (tid < M) s.v[tid] += fmin(s.dk[tid], D);
+    __syncthreads();
+    // ---- augment along the parent chain (thread 0; paths are short) ----
+    if (tid == 0) {
+      int delta = s.deficit[target];
+      int k = target;
+      int i = s.par_k[k];
+      int hops = 0;
+      while (true) {
+        const int pk = s.par_s[i];
+        if (pk < 0) { delta = min(delta, s.excess[i]); break; }
+        delta = min(delta, x[(long)i * M + pk]);
+        k = pk;
+        i = s.par_k[k];
+        if (++hops > n + M) { atomicOr(err, 4); delta = 0; break; }
+      }
+      if (delta > 0) {
+        k = target;
+        i = s.par_k[k];
+        s.deficit[target] -= delta;
+        while (true) {
+          x[(long)i * M + k] += delta;
+          const int pk = s.par_s[i];
+          if (pk < 0) { s.excess[i] -= delta; break; }
+          x[(long)i * M + pk] -= delta;
+          k = pk;
+          i = s.par_k[k];
+        }
+        s.ctl[0] -= delta;
+      } else {
+        atomicOr(err, 8);
+        s.ctl[0] = 0;
+      }
+    }
+    __threadfence_block();
+    __syncthreads();
+  }
+  if (s.ctl[0] > 0 && tid == 0) atomicOr(err, 16);
+  __syncthreads();
+  // ---- value and keypoint gradients from the (constant) plan T = x / (n * M) ----
+  const double unit = 1.0 / ((double)n * (double)M);
+  double tot = 0.0;
+  for (int o = tid; o < n * M; o += LOSS_THREADS) {
+    const int i = o / M, k = o - i * M;
+    const int f = x[o];
+    if (f) tot += (double)f * ot_cost(s, i, k);
+  }
+  tot = block_sum_d(tot, s.red_v) * unit;
+  if (tid == 0) parts[(long)b * 4 + 1] = tot;
+  const double gsc = 2.0 * unit * w_ot / (double)B;
+  for (int o = tid; o < M * 6; o += LOSS_THREADS) {
+    const int k = o / 6, q = o - k * 6;
+    double t = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const int f = x[(long)i * M + k];
+      if (f) t += (double)f * (s.Y[k * 6 + q] - s.P[i * 6 + q]);
+    }
+    const int side = q / 3, c = q - side * 3;
+    dkeypts[((long)(side == 0 ? b : B + b) * M + k) * 3 + c] = gsc * t;
+  }
+}
+
+// loss = mean_b mse + w_ot mean_b ot + w_int mean_b inter (train.py:143-150); out[0..3] = {loss, mse, ot, inter}
+__global__ void loss_total_kernel(int n_pairs, const double* __restrict__ parts, double w_ot, double w_int,
+                                  double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = 0; i < n_pairs; ++i) { a += parts[(long)i * 4]; b += parts[(long)i * 4 + 1]; c += parts[(long)i * 4 + 2]; }
+    a /= n_pairs; b /= n_pairs; c /= n_pairs;
+    out[0] = a + w_ot * b + w_int * c;
+    out[1] = a; out[2] = b; out[3] = c;
+  }
+}
+
+}  // namespace eqd
+
+extern "C" size_t eqd_losses_workspace_bytes(int32_t n_rec_nodes, int32_t n_pocket_total) {
+  const size_t a = ((size_t)(n_rec_nodes > 0 ? n_rec_nodes : 1) * 8 + 255) & ~(size_t)255;
+  const size_t f = ((size_t)(n_pocket_total > 0 ? n_pocket_total : 1) * EQD_HEADS * 4 + 255) & ~(size_t)255;
+  return a + f + 256;
+}
+
+// parts[B][4] = {mse, ot, intersection, -} per pair; total[4] = {loss, mean mse, mean ot, mean intersection};
+// dcoors [N_l][3] fp32 and dkeypts [2B][50][3] fp64 = gradients of `loss`; plan_flow (inside the workspace) keeps the
+// integer transport plans.  err_flags (device int, zeroed by the call) != 0 reports a pocket larger than 1024 or a solver
+// failure.
+extern "C" int eqd_losses(const eqd_graph* g, const float* pred_lig, const float* bound_lig, const float* bound_rec,
+                          const double* keypts, const int32_t* pocket_ptr, const float* pocket_lig,
+                          const float* pocket_rec, int32_t n_pocket_total, float w_ot, float w_int, float sigma,
+                          float surface_ct, void* workspace, size_t workspace_bytes, double* parts, double* total,
+                          float* dcoors, double* dkeypts, int32_t* err_flags, void* stream) {
+  if (!g || !pred_lig || !bound_lig || !bound_rec || !keypts || !pocket_ptr || !pocket_lig || !pocket_rec || !workspace ||
+      !parts || !total || !dcoors || !dkeypts || !err_flags)
+    return EQD_ERR_BAD_ARG;
+  const int n_rec = g->n_nodes - g->n_lig_nodes;
+  if (workspace_bytes < eqd_losses_workspace_bytes(n_rec, n_pocket_total)) return EQD_ERR_WORKSPACE;
+  if (g->n_pairs <= 0) return EQD_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+  double* wrec = reinterpret_cast<double*>(w);
+  int* flow = reinterpret_cast<int*>(w + (((size_t)(n_rec > 0 ? n_rec : 1) * 8 + 255) & ~(size_t)255));
+  cudaError_t me = cudaMemsetAsync(err_flags, 0, sizeof(int32_t), st);
+  if (me != cudaSuccess) return -(1000 + (int)me);
+  eqd::loss_mse_intersection_kernel<<<g->n_pairs, LOSS_THREADS, 0, st>>>(*g, pred_lig, bound_lig, bound_rec, (double)sigma,
+                                                                        (double)surface_ct, (double)w_int, wrec, parts,
+                                                                        dcoors);
+  EQD_CUDA_LAUNCH_CHECK();
+  size_t smem = sizeof(eqd::OtSmem);
+  EQD_SET_SMEM((eqd::ot_emd_kernel), smem);
+  eqd::ot_emd_kernel<<<g->n_pairs, LOSS_THREADS, smem, st>>>(g->n_pairs, pocket_ptr, pocket_lig, pocket_rec, keypts,
+                                                            (double)w_ot, flow, parts, dkeypts, err_flags);
+  EQD_CUDA_LAUNCH_CHECK();
+  eqd::loss_total_kernel<<<1, 32, 0, st>>>(g->n_pairs, parts, (double)w_ot, (double)w_int, total);
+  EQD_CUDA_LAUNCH_CHECK();
+  return EQD_OK;
+}

@@ -422,7 +422,7 @@ class IEGMNEngine:
 
     def forward(self, plan: GraphPlan, emb: torch.Tensor, layers: List[PackedLayer], head: PackedHead,
                 res_l, res_r, mu_l, mu_r, x_l, x_r, check_status: bool = True, log=None,
-                stage_timer=None, record_event: bool = True) -> Dict[str, torch.Tensor]:
+                stage_timer=None, record_event: bool = True, train_stash=None) -> Dict[str, torch.Tensor]:
         """One forward = ONE call into the library (eqd_iegmn_forward): the per-stage entry points are chained in C on
         the current stream out of a single workspace allocation.  EQD_PY_FORWARD=1 selects the stage-by-stage Python
         driver below instead (same kernels; used to A/B the two and by the per-stage tests)."""
@@ -431,10 +431,10 @@ class IEGMNEngine:
                 return self._forward_py(plan, emb, layers, head, res_l, res_r, mu_l, mu_r, x_l, x_r, check_status, log,
                                         stage_timer)
             return self._forward_native(plan, emb, layers, head, res_l, res_r, mu_l, mu_r, x_l, x_r, check_status, log,
-                                        stage_timer, record_event)
+                                        stage_timer, record_event, train_stash)
 
     def _forward_native(self, plan, emb, layers, head, res_l, res_r, mu_l, mu_r, x_l, x_r, check_status, log,
-                        stage_timer, record_event=True):
+                        stage_timer, record_event=True, train_stash=None):
         lib, dev = self.lib, self.device
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         N, B = plan.N, plan.n_pairs
@@ -460,6 +460,8 @@ class IEGMNEngine:
                         ('cov', cov), ('ymean', ymean)):
             setattr(io, name, t.data_ptr())
         io.layer0_fp32 = 1 if _LAYER0_FFMA else 0
+        if train_stash is not None:   # training: keep every layer's inputs for the backward kernels
+            io.train_stash, io.train_stash_bytes = train_stash.data_ptr(), int(train_stash.numel())
         events = stage_timer.new_forward(len(layers)) if stage_timer is not None else None
         io.stage_events = C.cast(events, C.c_void_p) if events is not None else None
         larr = (C.POINTER(nat.EqdLayerParams) * len(layers))(*[C.pointer(l.struct) for l in layers])

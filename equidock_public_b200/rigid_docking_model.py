@@ -15,11 +15,12 @@ Parameter names and shapes equal the reference's ``state_dict``, so 
 checkpoints load with ``strict=True``.  The graph argument may be a batched DGL heterograph
 (``train_utils.py:61-100``) or this package's DGL-free ``PairGraphBatch``.
 
-Scope of this engine: forward pass of the configuration the shipped checkpoints use
+Scope of this engine: forward AND backward of the configuration the shipped checkpoints use
 (``nonlin='lkyrelu'``, ``layer_norm='LN'``, ``layer_norm_coors='0'``, ``final_h_layer_norm='0'``,
 ``cross_msgs``, ``use_dist_in_layers``, ``rot_model='kb_att'``, ``fine_tune=False``, dropout inactive).
 Anything else raises ``NotImplementedError``; a missing CUDA library raises -- there is no CPU path.
-Outputs are not autograd-connected yet (backward kernels: SURVEY 8a "backward map", next round).
+In training mode (``model.train()`` with grad enabled) the outputs of ``Rigid_Body_Docking_Net.forward`` are
+autograd-connected: the whole path is one autograd node backed by the CUDA backward kernels (``training.py``).
 """
 import math  # noqa: F401  (re-exported, see module docstring)
 import sys  # noqa: F401
@@ -410,7 +411,28 @@ class Rigid_Body_Docking_Net(nn.Module):
         return GraphedForward(self, device_batch)
 
     def forward(self, batch_hetero_graph, epoch):
+        if (self.training or getattr(self, 'force_autograd', False)) and torch.is_grad_enabled():
+            return self._forward_autograd(batch_hetero_graph)
         return self._assemble(self.iegmn_original(batch_hetero_graph, epoch))
+
+    def _forward_autograd(self, batch_hetero_graph):
+        """Training mode (``model.train()``, src/train.py:64): the whole hot path is ONE autograd node whose backward is the
+        hand-written CUDA backward (``training.TrainEngine``), so ``loss.backward()`` (train.py:154) fills ``param.grad`` of
+        every parameter exactly like the reference's autograd graph does.  Outputs are autograd-connected views of the
+        node's four raw outputs.  Evaluation under ``torch.no_grad()`` / ``model.eval()`` keeps the inference path."""
+        from .training import autograd_forward
+        fwd, (coors, keypts, rot, trans) = autograd_forward(self, batch_hetero_graph, self.log)
+        plan = fwd['plan']
+        B, N_l = plan.n_pairs, plan.N_l
+        nl, nr = batch_hetero_graph.nodes[LIGAND].data, batch_hetero_graph.nodes[RECEPTOR].data
+        dt = nl['new_x'].dtype
+        x_fin = fwd['x64'].to(dt)
+        nl['x_iegmn_out'], nr['x_iegmn_out'] = x_fin[:N_l], x_fin[N_l:]
+        nl['hv_iegmn_out'], nr['hv_iegmn_out'] = fwd['h'][:N_l], fwd['h'][N_l:]
+        self.iegmn_original.last_outputs = fwd
+        keyp = keypts.to(dt)
+        return (list(torch.split(coors, plan.n_lig_list, dim=0)), list(keyp[:B].unbind(0)), list(keyp[B:].unbind(0)),
+                list(rot.unbind(0)), list(trans.unbind(0)))
 
     def _assemble(self, outputs):
         assert len(outputs) == 4

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define EQD_ABI_VERSION 6
+#define EQD_ABI_VERSION 7
 
 #define EQD_EDGE_FEATS 27     /* input_edge_feats_dim, protein_utils.py:71-86 + :373-389 */
 #define EQD_N_RBF 15          /* all_sigmas_dist = 1.5**s, rigid_docking_model.py:116 */
@@ -293,12 +293,107 @@ typedef struct eqd_forward_io {
    * on `stream`; NULL entries are skipped.  eqd_event_create / _elapsed_ms / _destroy wrap the CUDA calls.          */
   void* const* stage_events;
   int32_t layer0_fp32;        /* != 0: keep the 69-wide layer 0 on the fp32 CUDA-core kernels */
+  /* training: NULL, or eqd_forward_stash_bytes(g, n_layers) bytes of 256-byte aligned device memory that receives every
+   * layer's inputs and intermediate node tensors (layout: eqd_forward_stash_offsets) for the backward entry points */
+  void* train_stash;
+  size_t train_stash_bytes;
 } eqd_forward_io;
 
 size_t eqd_forward_workspace_bytes(const eqd_graph* g);
+size_t eqd_forward_stash_bytes(const eqd_graph* g, int32_t n_layers);
+/* out[9] = byte offsets / strides inside the stash: h0 [n][72] f32 | x[l] [n][3] f64 (offset, stride per layer; x[0] = the
+ * input coordinates) | h[l] [n][64] f32, l >= 1 (offset, stride) | aggr[l] [n][64] f32 (offset, stride) | mu[l] f32, row
+ * stride 72 for the 69-wide layer 0 and 64 otherwise (offset, stride) */
+int eqd_forward_stash_offsets(const eqd_graph* g, int32_t n_layers, size_t* out);
 int eqd_iegmn_forward(const eqd_graph* g, const eqd_layer_params* const* layers, int32_t n_layers,
                       const eqd_head_params* hp, const eqd_forward_io* io, void* workspace, size_t workspace_bytes,
                       void* stream);
+
+/* =====================================================================================================================
+ * BACKWARD of the path (training: BASELINE configs 3-4).  The reference has no backward code: these entry points are
+ * what a binding would call from torch.autograd.Function.backward in place of `loss.backward()` (src/train.py:154)
+ * walking rigid_docking_model.py in reverse.  Same conventions as above (device pointers, caller-owned buffers, stream).
+ * Flow for one batch: eqd_iegmn_forward with io->train_stash set -> (losses) -> eqd_bwd_head -> for every layer, last to
+ * first: eqd_project (recompute this layer's Psrc|Pdst|Q|K|V in fp32) -> eqd_bwd_node_mlp -> eqd_bwd_attention ->
+ * eqd_bwd_edge -> eqd_bwd_edge_gather -> eqd_bwd_project, each followed by eqd_tn_gemm + eqd_grad_reduce for its weight
+ * gradients -> eqd_bwd_embed.  All reductions run in a fixed order: gradients are bit-reproducible for a given batch.
+ * ================================================================================================================== */
+
+/* Generic weight-gradient reduction  partial[c][k][n] = alpha * sum_{rows of chunk c} X[row][k] * D[row][n]  (and, if
+ * colsum != NULL, colsum[c][n] = alpha * sum D[row][n]: the bias gradient).  K, ncols, ldx, ldd multiples of 4; X and D
+ * 16-byte aligned.  eqd_tn_partial_floats gives the size of `partial` (floats) and the chunking the kernel will use;
+ * colsum needs nchunks * ncols floats.  Second stage: eqd_grad_reduce.                                               */
+size_t eqd_tn_partial_floats(int64_t nrows, int32_t K, int32_t ncols, int32_t* rows_per_chunk_out, int32_t* nchunks_out);
+int eqd_tn_gemm(const float* X, int32_t ldx, int32_t K, const float* D, int32_t ldd, int32_t ncols, int64_t nrows,
+                float alpha, float* partial, float* colsum, int32_t* nchunks_out, void* stream);
+/* grad[dst_index[i]] += sum_{c < nchunks} partial[c * stride + src_index[i]]   (fixed order, fp64 accumulation): the
+ * deterministic second stage, and the scatter from the kernels' packed k-major panels to the state_dict layout.      */
+int eqd_grad_reduce(const float* partial, int32_t nchunks, int64_t stride, const int32_t* src_index,
+                    const int32_t* dst_index, int32_t n, float* grad, void* stream);
+
+/* Node update backward (:319-337).  w_node1_lin = node_mlp.0.weight as [dhp][2 dhp + 136] (rows = hidden unit, columns
+ * = the padded input blocks h | aggr | mu | h0(72)), w_node2_lin = node_mlp.4.weight as [64][dhp].  mu has row stride
+ * ldmu.  Outputs: dh_in [n][dhp] (overwritten: skip path + h block), daggr [n][64], dmu [n][dhp], dh0_acc [n][72]
+ * (accumulated), n5_out / du_out [n][dhp] (operands of the weight-gradient reductions), vec_partial
+ * [n_partials][144] = per-CTA partials of {d node_mlp.3.weight [72], d node_mlp.3.bias [72]}.                          */
+int eqd_bwd_node_mlp(const eqd_graph* g, const eqd_layer_params* p, const float* w_node1_lin, const float* w_node2_lin,
+                     const float* h_in, int32_t ldh, const float* aggr, const float* mu, int32_t ldmu, const float* h0,
+                     const float* dh_out, float* dh_in, float* daggr, float* dmu, float* dh0_acc, float* n5_out,
+                     float* du_out, float* vec_partial /* [148][144] */, int32_t* n_partials_out, void* stream);
+/* Cross attention backward (:46-64, 247-256): dmu [n][dhp] -> dP[:, 128:] = [dQpre | dKpre | dV] of the combined
+ * projection-gradient matrix dP [n][128 + 3 dhp].  proj = this layer's fp32 projections (eqd_project), mu the stashed
+ * attention output, rowstat [n][4] scratch.                                                                         */
+int eqd_bwd_attention(const eqd_graph* g, const eqd_layer_params* p, const float* proj, const float* mu, int32_t ldmu,
+                      const float* dmu, float* dP, float* rowstat, void* stream);
+/* Edge stage backward (:204-237, 263-292).  w2lin / w3lin = edge_mlp.4.weight / coors_mlp.0.weight [64][64] as in the
+ * state_dict.  Outputs per edge: ein [E][44] = [he | rbf | 0 0], n1, msg, dz3, dmsg, dz1 [E][64], dxrel [E][3] (fp64);
+ * vec_partial [n_partials][256] = per-CTA partials {d edge_mlp.3.weight [64], d edge_mlp.3.bias [64],
+ * d coors_mlp.4.weight [64], d coors_mlp.4.bias [1]}.                                                                */
+int eqd_bwd_edge(const eqd_graph* g, const eqd_layer_params* p, const float* w2lin, const float* w3lin, const float* proj,
+                 const double* x_in, const float* daggr, const double* dx_out, float* ein_out, float* n1_out,
+                 float* msg_out, float* dz3_out, float* dmsg_out, float* dz1_out, double* dxrel_out,
+                 float* vec_partial /* [148][256] */, int32_t* n_partials_out, void* stream);
+/* Per node: dP[:, 0:64] = sum over OUT-edges of dz1, dP[:, 64:128] = sum over IN-edges, dx_in = (1 - eta) dx_out +
+ * sum_out dxrel - sum_in dxrel.  out_ptr [n+1] / out_edge [E]: edges grouped by SOURCE node (ascending edge id).      */
+int eqd_bwd_edge_gather(const eqd_graph* g, const int32_t* out_ptr, const int32_t* out_edge, const float* dz1,
+                        const double* dxrel, const double* dx_out, float eta, float* dP, int32_t ldp, double* dx_in,
+                        void* stream);
+/* dh[n][0:dhp] += dP[n][:] . Wproj^T;  w_projT = eqd_layer_params.w_proj transposed, [128 + 3 dhp][dhp].            */
+int eqd_bwd_project(const eqd_graph* g, const eqd_layer_params* p, const float* w_projT, const float* dP, float* dh,
+                    void* stream);
+/* d residue_emb_layer.weight [21][64] += sum over nodes of that residue type of (dh0_acc + dh_layer0)[0:64].         */
+int eqd_bwd_embed(const eqd_graph* g, const float* res_lig, const float* res_rec, const float* dh0_acc,
+                  const float* dh_layer0, float* demb, void* stream);
+/* Keypoint read-out + Kabsch backward (:521-589, 657-665), fp64, incl. the 3x3 SVD backward (torch's svd_backward with
+ * the guard's gap as denominator).  See csrc/head.cu for the argument semantics.                                      */
+size_t eqd_bwd_head_workspace_bytes(int32_t n_nodes, int32_t n_node_tiles, int32_t n_pairs);
+int eqd_bwd_head(const eqd_graph* g, const eqd_head_params* hp, const float* h, const double* x, const double* cov,
+                 const float* x_lig_in, const float* dcoors, const double* dkeypts, const float* drot,
+                 const float* dtrans, void* workspace, size_t workspace_bytes, float* dh, double* dx, float* dpre,
+                 float* g_wkey, float* g_wquery, void* stream);
+
+/* ---- training losses on the device (src/train.py:41-49, 112-150; src/utils/ot_utils.py:5-29) ------------------------
+ * Per pair: MSE of the predicted ligand coordinates, body-intersection loss, pocket OT loss with the EXACT earth mover's
+ * distance (uniform marginals; successive shortest paths with potentials instead of POT's CPU network simplex), batch
+ * means combined with the reference's weights; plus the gradients w.r.t. the predicted coordinates and the keypoints. */
+size_t eqd_losses_workspace_bytes(int32_t n_rec_nodes, int32_t n_pocket_total);
+int eqd_losses(const eqd_graph* g, const float* pred_lig /*[N_l][3]*/, const float* bound_lig /*[N_l][3]*/,
+               const float* bound_rec /*[N_r][3]*/, const double* keypts /*[2B][50][3]*/,
+               const int32_t* pocket_ptr /*[B+1]*/, const float* pocket_lig, const float* pocket_rec /*[sum P][3]*/,
+               int32_t n_pocket_total, float pocket_ot_loss_weight, float intersection_loss_weight,
+               float intersection_sigma, float intersection_surface_ct, void* workspace, size_t workspace_bytes,
+               double* parts /*[B][4] mse, ot, intersection, -*/, double* total /*[4] loss, mse, ot, intersection*/,
+               float* dcoors /*[N_l][3]*/, double* dkeypts /*[2B][50][3]*/, int32_t* err_flags, void* stream);
+
+/* ---- optimiser side on the flat fp32 parameter / gradient buffers (src/train.py:156, 165, 302) -----------------------
+ * eqd_sqnorm_partials: partial[i] = sum of squares of slice i (n_partial <= 1024 doubles).  eqd_clip_adam: g *= scale_extra;
+ * clip_grad_norm_(max_norm) with the global norm sqrt(sum partial) * |scale_extra|; torch.optim.Adam step (L2 weight decay,
+ * bias correction at `step` >= 1); norm_out (device float, may be NULL) receives the pre-clip norm.                     */
+int eqd_sqnorm_partials(const float* g, int64_t n, double* partial, int32_t n_partial, void* stream);
+int eqd_clip_adam(float* w, float* g, float* m, float* v, int64_t n, const double* sq_partial, int32_t n_partial,
+                  float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                  float scale_extra, float* norm_out, void* stream);
+
 void* eqd_event_create(void);
 void eqd_event_destroy(void* event);
 float eqd_event_elapsed_ms(void* begin, void* end);

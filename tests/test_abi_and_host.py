@@ -48,7 +48,8 @@ def test_struct_layouts_are_natural_c_layouts():
     assert nat.EqdLayerParams.w_node1.offset == 144
     assert ctypes.sizeof(nat.EqdHeadParams) == 5 * 8 + 8
     assert nat.EqdHeadParams.m_qk.offset == 32 and nat.EqdHeadParams.leaky_slope.offset == 40
-    assert ctypes.sizeof(nat.EqdForwardIO) == 18 * 8 + 8 and nat.EqdForwardIO.stage_events.offset == 17 * 8
+    assert ctypes.sizeof(nat.EqdForwardIO) == 18 * 8 + 8 + 16 and nat.EqdForwardIO.stage_events.offset == 17 * 8
+    assert nat.EqdForwardIO.train_stash.offset == 19 * 8 and nat.EqdForwardIO.train_stash_bytes.offset == 20 * 8
     assert nat.EqdForwardIO.layer0_fp32.offset == 18 * 8
 
 
