@@ -331,7 +331,11 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = effective_cores()
-    pairs, _, _ = make_pairs(args, 0, world)
+    if args.workload == 'train':
+        import bench_train
+        pairs, _, _ = bench_train.make_train_pairs(args, 0, world, sys.modules[__name__])
+    else:
+        pairs, _, _ = make_pairs(args, 0, world)
     sample = len(pairs) if args.ref_sample <= 0 else min(args.ref_sample, len(pairs))
     pairs = pairs[:sample]
     pool = ReferencePool(cores, args.workload)

@@ -912,3 +912,100 @@ extern "C" int eqd_bwd_head(const eqd_graph* g, const eqd_head_params* hp, const
   EQD_CUDA_LAUNCH_CHECK();
   return EQD_OK;
 }
+
+// =====================================================================================================================
+// Batched RMSD meter: Meter_Unbound_Bound.update_rmsd (src/utils/eval.py:19-42) for every pair of a
+// batch in one launch -- ligand RMSD, receptor RMSD and the complex RMSD after a Kabsch superposition of the predicted
+// complex on the true one (rigid_transform_Kabsch_3D, src/utils/protein_utils.py:31-64; reflection fix :56-59), reusing
+// the 3x3 Jacobi SVD of the docking head.  One CTA per pair, fp64, fixed-order reductions.
+// =====================================================================================================================
+namespace eqd {
+
+__device__ __forceinline__ void block_sum_vec(double* v, int n, double (*sh)[12], int tid) {
+  __syncthreads();
+  for (int q = 0; q < n; ++q) sh[tid][q] = v[q];
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) {
+    if (tid < s)
+      for (int q = 0; q < n; ++q) sh[tid][q] += sh[tid + s][q];
+    __syncthreads();
+  }
+  for (int q = 0; q < n; ++q) v[q] = sh[0][q];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128)
+rmsd_meter_kernel(eqd_graph g, const float* __restrict__ lig_pred, const float* __restrict__ rec_pred,
+                  const float* __restrict__ lig_true, const float* __restrict__ rec_true, double* __restrict__ out /*[B][3]*/) {
+  __shared__ double sh[128][12];
+  __shared__ double Rm[9];
+  const int b = blockIdx.x, B = g.n_pairs, tid = threadIdx.x;
+  const int l0 = g.seg_ptr[b], l1 = g.seg_ptr[b + 1];
+  const int r0 = g.seg_ptr[B + b] - g.n_lig_nodes, r1 = g.seg_ptr[B + b + 1] - g.n_lig_nodes;
+  const int nl = l1 - l0, nr = r1 - r0, n = nl + nr;
+  auto P = [&](int i, int c) -> double { return i < nl ? (double)lig_pred[(long)(l0 + i) * 3 + c] : (double)rec_pred[(long)(r0 + i - nl) * 3 + c]; };
+  auto Q = [&](int i, int c) -> double { return i < nl ? (double)lig_true[(long)(l0 + i) * 3 + c] : (double)rec_true[(long)(r0 + i - nl) * 3 + c]; };
+  double a[12];
+  for (int q = 0; q < 12; ++q) a[q] = 0.0;
+  for (int i = tid; i < n; i += 128) {
+    double d2 = 0.0;
+    for (int c = 0; c < 3; ++c) {
+      const double p = P(i, c), q = Q(i, c);
+      a[c] += p;
+      a[3 + c] += q;
+      d2 += (p - q) * (p - q);
+    }
+    if (i < nl) a[6] += d2; else a[7] += d2;
+  }
+  block_sum_vec(a, 8, sh, tid);
+  const double cp[3] = {a[0] / n, a[1] / n, a[2] / n}, cq[3] = {a[3] / n, a[4] / n, a[5] / n};
+  const double lig_rmsd = sqrt(a[6] / (nl > 0 ? nl : 1)), rec_rmsd = sqrt(a[7] / (nr > 0 ? nr : 1));
+  double h[12];
+  for (int q = 0; q < 12; ++q) h[q] = 0.0;
+  for (int i = tid; i < n; i += 128)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) h[r * 3 + c] += (P(i, r) - cp[r]) * (Q(i, c) - cq[c]);     // H = Am Bm^T (:48)
+  block_sum_vec(h, 9, sh, tid);
+  if (tid == 0) {
+    double A[9], U[9], S[3], V[9];
+    for (int q = 0; q < 9; ++q) A[q] = h[q];
+    svd3(A, U, S, V);
+    double R[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) R[r * 3 + c] = V[r * 3] * U[c * 3] + V[r * 3 + 1] * U[c * 3 + 1] + V[r * 3 + 2] * U[c * 3 + 2];   // Vt.T @ U.T
+    const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+    if (det < 0.0)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) R[r * 3 + c] = V[r * 3] * U[c * 3] + V[r * 3 + 1] * U[c * 3 + 1] - V[r * 3 + 2] * U[c * 3 + 2];
+    for (int q = 0; q < 9; ++q) Rm[q] = R[q];
+  }
+  __syncthreads();
+  double e[12];
+  for (int q = 0; q < 12; ++q) e[q] = 0.0;
+  for (int i = tid; i < n; i += 128) {
+    const double px = P(i, 0) - cp[0], py = P(i, 1) - cp[1], pz = P(i, 2) - cp[2];
+    for (int r = 0; r < 3; ++r) {
+      const double v = Rm[r * 3] * px + Rm[r * 3 + 1] * py + Rm[r * 3 + 2] * pz + cq[r] - Q(i, r);   // R p + t, t = -R cA + cB
+      e[0] += v * v;
+    }
+  }
+  block_sum_vec(e, 1, sh, tid);
+  if (tid == 0) {
+    out[(long)b * 3 + 0] = sqrt(e[0] / (n > 0 ? n : 1));
+    out[(long)b * 3 + 1] = lig_rmsd;
+    out[(long)b * 3 + 2] = rec_rmsd;
+  }
+}
+
+}  // namespace eqd
+
+// out[b] = {complex_rmsd, ligand_rmsd, receptor_rmsd} of pair b.  Coordinates are fp32 [N_l][3] / [N_r][3] in batch order
+// (receptor arrays indexed by receptor-local node id).
+extern "C" int eqd_rmsd_meter(const eqd_graph* g, const float* lig_pred, const float* rec_pred, const float* lig_true,
+                              const float* rec_true, double* out, void* stream) {
+  if (!g || !lig_pred || !rec_pred || !lig_true || !rec_true || !out) return EQD_ERR_BAD_ARG;
+  if (g->n_pairs <= 0) return EQD_OK;
+  eqd::rmsd_meter_kernel<<<g->n_pairs, 128, 0, (cudaStream_t)stream>>>(*g, lig_pred, rec_pred, lig_true, rec_true, out);
+  EQD_CUDA_LAUNCH_CHECK();
+  return EQD_OK;
+}

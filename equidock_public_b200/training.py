@@ -410,3 +410,91 @@ def autograd_forward(model, graph, log=None):
     holder = {'engine': eng, 'graph': graph, 'log': log}
     outs = _HotPath.apply(holder, *eng.layout.params)
     return holder['fwd'], outs
+
+
+# ---- fused data-parallel training step -------------------------------------------------------------------------------
+
+def allreduce_buckets(flat: torch.Tensor, buckets, world: int, group=None):
+    """Sum-all-reduce of a flat gradient buffer bucket by bucket (same result as one all-reduce of the whole buffer:
+    buckets are disjoint slices).  Host-side helper shared by the trainer and the gloo test."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    for _, lo, hi in buckets:
+        dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=group)
+
+
+class DataParallelTrainer:
+    """One training step of the reference (src/train.py:88-169) on the engine, data-parallel over pairs:
+
+        forward (stash) -> device losses (MSE + exact-EMD OT + intersection, losses.cu) -> CUDA backward into ONE flat
+        fp32 gradient -> per-bucket NCCL all-reduce on a side stream, launched as soon as a bucket's last kernel is
+        queued (head first: 49 % of the parameters; then the layers last to first) so that it overlaps the rest of the
+        backward -> global-norm partials -> fused clip_grad_norm_ + Adam on the flat parameter buffer.
+
+    Each rank normalises its loss by its LOCAL pair count (train.py:143-146); gradients are averaged over ranks, which is
+    the reference's global-batch mean when ranks hold equally many pairs.  The model's parameters are re-pointed at
+    slices of one flat buffer (``param.data`` views), so the update is a single kernel and the all-reduce needs no
+    packing."""
+
+    def __init__(self, model, lr: float, weight_decay: float = 0.0, clip: float = 100.0, betas=(0.9, 0.999), eps: float = 1e-8,
+                 pocket_ot_loss_weight: float = 1.0, intersection_loss_weight: float = 10.0, intersection_sigma: float = 25.0,
+                 intersection_surface_ct: float = 10.0, world: int = 1, group=None):
+        self.model = model.train()
+        self.engine = TrainEngine(model)
+        self.layout = self.engine.layout
+        dev = self.engine.device
+        self.device, self.world, self.group = dev, int(world), group
+        self.flat_w = torch.empty(self.layout.total, dtype=_f32, device=dev)
+        with torch.no_grad():
+            for p, v in zip(self.layout.params, self.layout.views(self.flat_w)):
+                v.copy_(p.detach().to(_f32))
+                p.data = v                                       # parameters now live in the flat buffer
+        self.m = torch.zeros_like(self.flat_w)
+        self.v = torch.zeros_like(self.flat_w)
+        self.flat_g = torch.zeros_like(self.flat_w)
+        self.sq = torch.empty(256, dtype=torch.float64, device=dev)
+        self.norm = torch.zeros(1, dtype=_f32, device=dev)
+        self.hp = dict(lr=float(lr), wd=float(weight_decay), clip=float(clip), b1=float(betas[0]), b2=float(betas[1]), eps=float(eps))
+        self.loss_args = (pocket_ot_loss_weight, intersection_loss_weight, intersection_sigma, intersection_surface_ct)
+        self.steps = 0
+        self.comm = torch.cuda.Stream(dev) if self.world > 1 else None
+        self.lib = nat.load()
+
+    def invalidate_packed(self):
+        for lay in self.model.iegmn_original.iegmn_layers:
+            lay._packed = None
+        self.model.iegmn_original._head = None
+        self.engine._packs.clear()
+
+    def step(self, graph, targets) -> Dict:
+        from .losses import device_losses
+        dev, eng = self.device, self.engine
+        with torch.cuda.device(dev):
+            compute = torch.cuda.current_stream(dev)
+            fwd = eng.forward(graph, self.model.log)
+            res = device_losses(fwd['plan'], fwd['ligand_coors'], fwd['keypts'], targets, *self.loss_args)
+            self.flat_g.zero_()                                  # optimizer.zero_grad() (train.py:88)
+
+            def bucket_done(label, lo, hi):
+                if self.world <= 1:
+                    return
+                import torch.distributed as dist
+                ev = torch.cuda.Event()
+                ev.record(compute)
+                with torch.cuda.stream(self.comm):
+                    self.comm.wait_event(ev)
+                    dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+
+            eng.backward(fwd, res['dcoors'], res['dkeypts'], flat=self.flat_g, on_bucket_done=bucket_done)
+            if self.world > 1:
+                compute.wait_stream(self.comm)
+            st = C.c_void_p(compute.cuda_stream)
+            self.steps += 1
+            nat.check(self.lib.eqd_sqnorm_partials(nat.ptr(self.flat_g), self.layout.total, nat.ptr(self.sq), 256, st), 'eqd_sqnorm_partials')
+            h = self.hp
+            nat.check(self.lib.eqd_clip_adam(nat.ptr(self.flat_w), nat.ptr(self.flat_g), nat.ptr(self.m), nat.ptr(self.v),
+                                             self.layout.total, nat.ptr(self.sq), 256, h['clip'], h['lr'], h['b1'], h['b2'], h['eps'],
+                                             h['wd'], self.steps, 1.0 / self.world, nat.ptr(self.norm), st), 'eqd_clip_adam')
+            self.invalidate_packed()
+        return {'loss': res['total'], 'grad_norm': self.norm, 'err': res['err'], 'fwd': fwd}

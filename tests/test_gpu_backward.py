@@ -22,6 +22,8 @@ PAIR = {'db5': '1QA9', 'dips': 'kq_1kq1.pdb1_2.dill'}
 
 
 def _np(t):
+    if isinstance(t, np.ndarray):
+        return t.astype(np.float64)
     return t.detach().cpu().numpy().astype(np.float64)
 
 
@@ -265,3 +267,68 @@ def test_device_losses_vs_oracle(n_pocket, cuda_device):
             pass
         else:
             assert _rel(ours_r, yr.grad.numpy()) < 1e-7
+
+
+def test_rmsd_meter_kernel_vs_reference_definition(cuda_device):
+    """eval.Meter_Unbound_Bound (batched kernel) == the numpy restatement of src/utils/eval.py:19-42 (oracle complex_rmsd),
+    incl. a pair whose best superposition is a reflection before the fix (:56-59)."""
+    from equidock_public_b200.eval import Meter_Unbound_Bound
+    from equidock_public_b200.engine import GraphPlan
+    rng = np.random.default_rng(3)
+    sizes = [(30, 41), (128, 7), (5, 300)]
+    pairs = [synthetic.synthetic_pair(rng, a, b, 4) for a, b in sizes]
+    plan = GraphPlan.from_graph(gio.make_batch(pairs, cuda_device), cuda_device)
+    lt = [rng.normal(0, 10, (a, 3)).astype(np.float32) for a, b in sizes]
+    rt = [rng.normal(0, 10, (b, 3)).astype(np.float32) for a, b in sizes]
+    lp, rp = [], []
+    for i, (a, b) in enumerate(sizes):
+        R, tv = synthetic.random_rigid(rng, 30.0)
+        if i == 1:
+            R = R @ np.diag([1, 1, -1]).astype(np.float32)       # mirrored prediction
+        lp.append(((R @ lt[i].T).T + tv + rng.normal(0, 0.7, (a, 3))).astype(np.float32))
+        rp.append(((R @ rt[i].T).T + tv + rng.normal(0, 0.7, (b, 3))).astype(np.float32))
+    tt = lambda L: [torch.from_numpy(x).to(cuda_device) for x in L]
+    meter = Meter_Unbound_Bound()
+    out = meter.update_rmsd_batch(plan, tt(lp), tt(rp), tt(lt), tt(rt)).cpu().numpy()
+    for i in range(3):
+        f = lambda a: a.astype(np.float64)
+        ref = orc.complex_rmsd(f(lp[i]), f(rp[i]), f(lt[i]), f(rt[i]))
+        assert abs(out[i, 0] - ref) < 1e-9 * max(1, ref)
+        assert abs(out[i, 1] - np.sqrt(((f(lp[i]) - f(lt[i])) ** 2).sum(1).mean())) < 1e-9 * max(1.0, out[i, 1])
+    single = Meter_Unbound_Bound().update_rmsd(tt(lp)[0], tt(rp)[0], tt(lt)[0], tt(rt)[0])
+    assert abs(single - out[0, 0]) < 1e-12
+
+
+def test_fused_trainer_step_equals_autograd_plus_torch_adam(cuda_device):
+    """DataParallelTrainer.step (device losses, CUDA backward into the flat buffer, fused clip + Adam) == the reference's
+    loop shape: model.train(); outputs -> the same losses through torch autograd on our outputs -> loss.backward() ->
+    clip_grad_norm_ -> torch.optim.Adam.step(), for two consecutive steps."""
+    from equidock_public_b200.losses import PocketBatch, device_losses
+    from equidock_public_b200.training import DataParallelTrainer
+    import copy
+    rng = np.random.default_rng(12)
+    sizes = [(60, 75), (90, 50)]
+    pairs = [synthetic.synthetic_pair(rng, a, b, 10) for a, b in sizes]
+    m1 = gio.build_model('db5', cuda_device).train()
+    m2 = gio.build_model('db5', cuda_device).train()
+    g = gio.make_batch(pairs, cuda_device)
+    bl = [torch.from_numpy(p[0]['x']) for p in pairs]
+    br = [torch.from_numpy(p[1]['x'] + 8.0) for p in pairs]
+    pk = [torch.from_numpy((0.5 * (p[0]['x'][:9] + p[1]['x'][:9] + 8.0)).astype(np.float32)) for p in pairs]
+    tgt = PocketBatch(bl, br, pk, pk, cuda_device)
+    tr = DataParallelTrainer(m1, lr=1e-3, weight_decay=1e-4, clip=100.0)
+    opt = torch.optim.Adam(m2.parameters(), lr=1e-3, weight_decay=1e-4)
+    for step in range(2):
+        r1 = tr.step(g, tgt)
+        opt.zero_grad()
+        coors, kl, kr, _, _ = m2(g, epoch=0)
+        plan = m2.iegmn_original.last_outputs['plan']
+        res = device_losses(plan, torch.cat(coors), torch.cat([torch.stack(kl), torch.stack(kr)]).double(), tgt, 1.0, 10.0, 25.0, 10.0)
+        # route the device-loss gradients through autograd: loss surrogate = <outputs, dloss/doutputs>
+        sur = (torch.cat(coors) * res['dcoors']).sum() + (torch.cat([torch.stack(kl), torch.stack(kr)]).double() * res['dkeypts']).sum()
+        sur.backward()
+        torch.nn.utils.clip_grad_norm_(m2.parameters(), max_norm=100.0)
+        opt.step()
+        assert abs(float(r1['loss'][0]) - float(res['total'][0])) < 1e-6 * max(1.0, abs(float(res['total'][0])))
+    for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert (p1 - p2).abs().max().item() < 5e-6, n1
