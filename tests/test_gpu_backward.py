@@ -74,6 +74,8 @@ def test_backward_stage_by_stage_vs_manual_oracle(ds, cuda_device):
         report.append(f'{tag:34s} rel {r:.2e}  max|ref| {np.abs(ref).max():.3e}')
         worst = max(worst, r / tol)
 
+    import atexit
+    atexit.register(lambda: print('\n'.join(report)))
     head = [s for s in stages if s.get('head')][0]
     chk('head dh', cap[0]['dh'], np.concatenate(head['dh']))
     chk('head dx', cap[0]['dx'], np.concatenate(head['dx']))
