@@ -34,6 +34,7 @@ class ParamLayout:
         self.buckets: List[tuple] = []          # (label, lo, hi) contiguous slices, in completion order
         self.module_bucket: Dict[int, str] = {}  # id(layer module) -> its bucket label
         self.total = 0
+        self._offs: List[int] = []
 
         def add(prefix, module, label):
             lo = self.total
@@ -42,7 +43,9 @@ class ParamLayout:
                     continue
                 seen.add(id(p))
                 self.entries.append((f'{prefix}{n}', p))
-                self.total += p.numel()
+                self._offs.append(self.total)
+                self.total += (p.numel() + 63) & ~63       # every parameter starts on a 256-byte boundary: the kernels
+                                                           # read weights 16 bytes at a time straight from the flat buffer
             if self.total > lo:
                 self.buckets.append((label, lo, self.total))
                 self.module_bucket[id(module)] = label
@@ -57,13 +60,11 @@ class ParamLayout:
         add('iegmn_original.residue_emb_layer.', iegmn.residue_emb_layer, 'emb')
         self.offset: Dict[int, int] = {}
         self.name_offset: Dict[str, int] = {}
-        o = 0
-        for name, p in self.entries:
+        for (name, p), o in zip(self.entries, self._offs):
             self.offset[id(p)] = o
             self.name_offset[name] = o
-            o += p.numel()
-        assert o == self.total
         self.params = [p for _, p in self.entries]
+        self.n_param_elements = sum(p.numel() for p in self.params)
 
     def views(self, flat: torch.Tensor) -> List[torch.Tensor]:
         return [flat[self.offset[id(p)]:self.offset[id(p)] + p.numel()].view(p.shape) for p in self.params]
