@@ -87,6 +87,9 @@ PROTOTYPES = {
     'eqd_bwd_head': (C.c_int, [_G, _H] + [_vp] * 9 + [C.c_size_t] + [_vp] * 6),
     'eqd_losses_workspace_bytes': (C.c_size_t, [_i32, _i32]),
     'eqd_losses': (C.c_int, [_G] + [_vp] * 7 + [_i32, _f32, _f32, _f32, _f32, _vp, C.c_size_t] + [_vp] * 6),
+    'eqd_graph_build_workspace_bytes': (C.c_size_t, [_i32]),
+    'eqd_graph_build_knn': (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
+    'eqd_graph_build_edges': (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'eqd_rmsd_meter': (C.c_int, [_G, _vp, _vp, _vp, _vp, _vp, _vp]),
     'eqd_sqnorm_partials': (C.c_int, [_vp, C.c_int64, _vp, _i32, _vp]),
     'eqd_clip_adam': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp, _vp]),

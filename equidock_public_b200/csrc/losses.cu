@@ -94,11 +94,14 @@ struct OtSmem {
   double u[OT_MAX_POCKET], ds[OT_MAX_POCKET];
   double v[EQD_HEADS], dk[EQD_HEADS];
   int excess[OT_MAX_POCKET], par_s[OT_MAX_POCKET];
-  int deficit[EQD_HEADS], par_k[EQD_HEADS];
+  int exl[OT_MAX_POCKET], expos[OT_MAX_POCKET];   // compact list of the sources that still have excess, and its inverse
+  int act[OT_MAX_POCKET];                          // sources reached by the sink settled last
+  int deficit[EQD_HEADS], par_k[EQD_HEADS], fl_cnt[EQD_HEADS];
   unsigned char vis_s[OT_MAX_POCKET], vis_k[EQD_HEADS + 14];
   double red_v[LOSS_THREADS];
   int red_i[LOSS_THREADS];
-  int ctl[4];
+  int ctl[8];                                      // 0 mass left, 1 |exl|, 2 |act|, 3 settled node, 4 target
+  double ctl_d[2];
 };
 
 __device__ __forceinline__ double ot_cost(const OtSmem& s, int i, int k) {
@@ -113,11 +116,18 @@ __device__ __forceinline__ double ot_cost(const OtSmem& s, int i, int k) {
   return c;
 }
 
-// One CTA per pair.  flow[pocket_ptr[b] .. ][50] (int32, global) = transported mass in units of 1/(n*50).
+// One CTA per pair: successive shortest augmenting paths with node potentials on the transport problem scaled to
+// integers (supply 50 per pocket point, demand n per keypoint, n * 50 units in all).  Because forward arcs form a
+// complete bipartite graph and backward arcs (k -> i, flow x_ik > 0) have reduced cost 0 by complementary slackness,
+// Dijkstra only ever has to SETTLE SINKS (<= 50 pops per augmentation): settling sink k reaches the sources feeding it
+// (kept as a per-sink list, maintained by the augmenting thread), and those relax the other sinks.  All minima are
+// taken lexicographically over (value, index), so the result does not depend on list or thread order.
+// flow[(p0 + i) * 50 + k] (int32, global) = x_ik;  lists / pos: per-sink source lists and their inverse (global).
 __global__ void __launch_bounds__(LOSS_THREADS)
 ot_emd_kernel(int n_pairs, const int* __restrict__ pocket_ptr, const float* __restrict__ pocket_lig,
               const float* __restrict__ pocket_rec, const double* __restrict__ keypts, double w_ot,
-              int* __restrict__ flow, double* __restrict__ parts, double* __restrict__ dkeypts, int* __restrict__ err) {
+              int* __restrict__ flow, int* __restrict__ lists, int* __restrict__ lpos, double* __restrict__ parts,
+              double* __restrict__ dkeypts, int* __restrict__ err) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   OtSmem& s = *reinterpret_cast<OtSmem*>(smem_raw);
   const int b = blockIdx.x, tid = threadIdx.x, B = n_pairs;
@@ -145,81 +155,99 @@ ot_emd_kernel(int n_pairs, const int* __restrict__ pocket_ptr, const float* __re
     s.Y[k * 6 + 3 + c] = keypts[((long)(B + b) * M + k) * 3 + c];
   }
   int* x = flow + (long)p0 * M;
-  for (int o = tid; o < n * M; o += LOSS_THREADS) x[o] = 0;
+  int* fl = lists + (long)p0 * M;      // fl[k * n + idx]: sources with x_ik > 0
+  int* pos = lpos + (long)p0 * M;      // pos[i * M + k]: index of i in list k, or -1
+  for (int o = tid; o < n * M; o += LOSS_THREADS) { x[o] = 0; pos[o] = -1; }
   __syncthreads();
   for (int i = tid; i < n; i += LOSS_THREADS) {     // u_i = min_k C_ik, v = 0: all reduced costs >= 0
     double mn = INFINITY;
     for (int k = 0; k < M; ++k) mn = fmin(mn, ot_cost(s, i, k));
     s.u[i] = mn;
     s.excess[i] = M;
+    s.exl[i] = i;
+    s.expos[i] = i;
   }
-  if (tid < M) { s.v[tid] = 0.0; s.deficit[tid] = n; }
-  if (tid == 0) s.ctl[0] = n * M;                    // mass still to ship
+  if (tid < M) { s.v[tid] = 0.0; s.deficit[tid] = n; s.fl_cnt[tid] = 0; }
+  if (tid == 0) { s.ctl[0] = n * M; s.ctl[1] = n; }
   __syncthreads();
   const long max_aug = 64L * (n + M) + 1024;
   for (long it = 0; it < max_aug && s.ctl[0] > 0; ++it) {
-    // ---- multi-source Dijkstra on reduced costs; all sources with excess start at distance 0 and are settled at once ----
+    const int nex = s.ctl[1];
     for (int i = tid; i < n; i += LOSS_THREADS) {
       const bool ex = s.excess[i] > 0;
       s.ds[i] = ex ? 0.0 : INFINITY;
       s.vis_s[i] = ex ? 1 : 0;
       s.par_s[i] = -1;
     }
-    if (tid < M) { s.vis_k[tid] = 0; }
-    __syncthreads();
-    if (tid < M) {                                   // dk[k] = min over excess sources of rc_ik (ties: lowest i)
-      const int k = tid;
+    // dk[k] = min over the sources with excess of the reduced cost: 2 threads per sink, merged lexicographically
+    {
+      const int k = tid & 63, part = tid >> 6;
       double best = INFINITY;
-      int bi = -1;
-      for (int i = 0; i < n; ++i)
-        if (s.excess[i] > 0) {
+      int bi = 0x7fffffff;
+      if (k < M)
+        for (int q = part; q < nex; q += 2) {
+          const int i = s.exl[q];
           const double rc = fmax(ot_cost(s, i, k) - s.u[i] - s.v[k], 0.0);
-          if (rc < best) { best = rc; bi = i; }
+          if (rc < best || (rc == best && i < bi)) { best = rc; bi = i; }
         }
-      s.dk[k] = best;
-      s.par_k[k] = bi;
+      s.red_v[tid] = best;
+      s.red_i[tid] = bi;
+      __syncthreads();
+      if (tid < M) {
+        double o2 = s.red_v[tid + 64];
+        int i2 = s.red_i[tid + 64];
+        if (o2 < best || (o2 == best && i2 < bi)) { best = o2; bi = i2; }
+        s.dk[tid] = best;
+        s.par_k[tid] = bi;
+        s.vis_k[tid] = 0;
+      }
+      __syncthreads();
     }
-    __syncthreads();
     int target = -1;
     double D = 0.0;
-    for (int guard = 0; guard < n + M + 2; ++guard) {
-      // argmin over unvisited nodes (sinks first on ties, then lowest index: deterministic)
-      double bv = INFINITY;
-      int bidx = -1;                                 // sink k -> k ; source i -> M + i
-      if (tid < M && !s.vis_k[tid]) { bv = s.dk[tid]; bidx = tid; }
-      for (int i = tid; i < n; i += LOSS_THREADS)
-        if (!s.vis_s[i] && s.ds[i] < bv) { bv = s.ds[i]; bidx = M + i; }
-      s.red_v[tid] = bv;
-      s.red_i[tid] = bidx;
-      __syncthreads();
-      for (int st = LOSS_THREADS / 2; st > 0; st >>= 1) {
-        if (tid < st) {
-          const double ov = s.red_v[tid + st];
-          const int oi = s.red_i[tid + st];
-          if (oi >= 0 && (s.red_i[tid] < 0 || ov < s.red_v[tid] || (ov == s.red_v[tid] && oi < s.red_i[tid]))) {
-            s.red_v[tid] = ov;
-            s.red_i[tid] = oi;
-          }
+    for (int pop = 0; pop <= M; ++pop) {
+      if (tid < 32) {                                // warp 0: lexicographic argmin over the unsettled sinks
+        double bv = INFINITY;
+        int bk = 0x7fffffff;
+        for (int k = tid; k < M; k += 32)
+          if (!s.vis_k[k] && (s.dk[k] < bv || (s.dk[k] == bv && k < bk))) { bv = s.dk[k]; bk = k; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+          if (ov < bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
         }
-        __syncthreads();
+        if (tid == 0) { s.ctl[3] = bk; s.ctl_d[0] = bv; s.ctl[2] = 0; }
       }
-      const int node = s.red_i[0];
-      const double dist = s.red_v[0];
       __syncthreads();
-      if (node < 0 || !(dist < INFINITY)) break;     // no augmenting path (cannot happen while mass remains)
-      if (node < M) {                                // a sink is settled
-        const int k = node;
-        if (s.deficit[k] > 0) { target = k; D = dist; break; }
-        if (tid == 0) s.vis_k[k] = 1;
-        for (int i = tid; i < n; i += LOSS_THREADS)  // backward arcs k -> i carry reduced cost 0 (complementary slackness)
-          if (!s.vis_s[i] && x[(long)i * M + k] > 0 && dist < s.ds[i]) { s.ds[i] = dist; s.par_s[i] = k; }
-      } else {                                       // a source is settled: relax its forward arcs
-        const int i = node - M;
-        if (tid == 0) s.vis_s[i] = 1;
-        if (tid < M && !s.vis_k[tid]) {
-          const double nd = dist + fmax(ot_cost(s, i, tid) - s.u[i] - s.v[tid], 0.0);
-          if (nd < s.dk[tid]) { s.dk[tid] = nd; s.par_k[tid] = i; }
+      const int k = s.ctl[3];
+      const double dist = s.ctl_d[0];
+      if (k >= M || !(dist < INFINITY)) break;       // no augmenting path (cannot happen while mass remains)
+      if (s.deficit[k] > 0) { target = k; D = dist; break; }
+      // settle sink k: the sources feeding it become reachable at the same distance (backward arcs cost 0)
+      const int cnt = s.fl_cnt[k];
+      for (int q = tid; q < cnt; q += LOSS_THREADS) {
+        const int i = fl[(long)k * n + q];
+        if (!s.vis_s[i]) {
+          s.vis_s[i] = 1;
+          s.ds[i] = dist;
+          s.par_s[i] = k;
+          s.act[atomicAdd(&s.ctl[2], 1)] = i;
         }
+      }
+      if (tid == 0) s.vis_k[k] = 1;
+      __syncthreads();
+      const int nact = s.ctl[2];
+      if (tid < M && !s.vis_k[tid] && nact > 0) {    // relax the forward arcs of the newly reached sources
+        double best = s.dk[tid];
+        int bi = s.par_k[tid];
+        for (int q = 0; q < nact; ++q) {
+          const int i = s.act[q];
+          const double nd = dist + fmax(ot_cost(s, i, tid) - s.u[i] - s.v[tid], 0.0);
+          if (nd < best || (nd == best && i < bi)) { best = nd; bi = i; }
+        }
+        s.dk[tid] = best;
+        s.par_k[tid] = bi;
       }
       __syncthreads();
     }
@@ -228,29 +256,50 @@ ot_emd_kernel(int n_pairs, const int* __restrict__ pocket_ptr, const float* __re
     for (int i = tid; i < n; i += LOSS_THREADS) s.u[i] -= fmin(s.ds[i], D);
     if (tid < M) s.v[tid] += fmin(s.dk[tid], D);
     __syncthreads();
-    // ---- augment along the parent chain (thread 0; paths are short) ----
+    // ---- augment along the parent chain and maintain the lists (one thread: deterministic) ----
     if (tid == 0) {
       int delta = s.deficit[target];
-      int k = target;
-      int i = s.par_k[k];
-      int hops = 0;
+      int k = target, i = s.par_k[k], hops = 0;
       while (true) {
         const int pk = s.par_s[i];
         if (pk < 0) { delta = min(delta, s.excess[i]); break; }
         delta = min(delta, x[(long)i * M + pk]);
         k = pk;
         i = s.par_k[k];
-        if (++hops > n + M) { atomicOr(err, 4); delta = 0; break; }
+        if (++hops > 2 * M + 2) { atomicOr(err, 4); delta = 0; break; }
       }
       if (delta > 0) {
         k = target;
         i = s.par_k[k];
         s.deficit[target] -= delta;
         while (true) {
-          x[(long)i * M + k] += delta;
+          int& xf = x[(long)i * M + k];
+          if (xf == 0) {                             // i starts feeding k
+            const int c = s.fl_cnt[k]++;
+            fl[(long)k * n + c] = i;
+            pos[(long)i * M + k] = c;
+          }
+          xf += delta;
           const int pk = s.par_s[i];
-          if (pk < 0) { s.excess[i] -= delta; break; }
-          x[(long)i * M + pk] -= delta;
+          if (pk < 0) {
+            s.excess[i] -= delta;
+            if (s.excess[i] == 0) {                  // drop i from the excess list (swap with the last entry)
+              const int q = s.expos[i], last = s.exl[s.ctl[1] - 1];
+              s.exl[q] = last;
+              s.expos[last] = q;
+              s.ctl[1] -= 1;
+            }
+            break;
+          }
+          int& xb = x[(long)i * M + pk];
+          xb -= delta;
+          if (xb == 0) {                             // i stops feeding pk
+            const int q = pos[(long)i * M + pk], c = --s.fl_cnt[pk];
+            const int last = fl[(long)pk * n + c];
+            fl[(long)pk * n + q] = last;
+            pos[(long)last * M + pk] = q;
+            pos[(long)i * M + pk] = -1;
+          }
           k = pk;
           i = s.par_k[k];
         }
@@ -305,7 +354,7 @@ __global__ void loss_total_kernel(int n_pairs, const double* __restrict__ parts,
 extern "C" size_t eqd_losses_workspace_bytes(int32_t n_rec_nodes, int32_t n_pocket_total) {
   const size_t a = ((size_t)(n_rec_nodes > 0 ? n_rec_nodes : 1) * 8 + 255) & ~(size_t)255;
   const size_t f = ((size_t)(n_pocket_total > 0 ? n_pocket_total : 1) * EQD_HEADS * 4 + 255) & ~(size_t)255;
-  return a + f + 256;
+  return a + 3 * f + 256;      // flows, per-sink source lists, list positions
 }
 
 // parts[B][4] = {mse, ot, intersection, -} per pair; total[4] = {loss, mean mse, mean ot, mean intersection};
@@ -326,7 +375,10 @@ extern "C" int eqd_losses(const eqd_graph* g, const float* pred_lig, const float
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
   double* wrec = reinterpret_cast<double*>(w);
+  const size_t fbytes = ((size_t)(n_pocket_total > 0 ? n_pocket_total : 1) * EQD_HEADS * 4 + 255) & ~(size_t)255;
   int* flow = reinterpret_cast<int*>(w + (((size_t)(n_rec > 0 ? n_rec : 1) * 8 + 255) & ~(size_t)255));
+  int* lists = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(flow) + fbytes);
+  int* lpos = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(lists) + fbytes);
   cudaError_t me = cudaMemsetAsync(err_flags, 0, sizeof(int32_t), st);
   if (me != cudaSuccess) return -(1000 + (int)me);
   eqd::loss_mse_intersection_kernel<<<g->n_pairs, LOSS_THREADS, 0, st>>>(*g, pred_lig, bound_lig, bound_rec, (double)sigma,
@@ -336,7 +388,7 @@ extern "C" int eqd_losses(const eqd_graph* g, const float* pred_lig, const float
   size_t smem = sizeof(eqd::OtSmem);
   EQD_SET_SMEM((eqd::ot_emd_kernel), smem);
   eqd::ot_emd_kernel<<<g->n_pairs, LOSS_THREADS, smem, st>>>(g->n_pairs, pocket_ptr, pocket_lig, pocket_rec, keypts,
-                                                            (double)w_ot, flow, parts, dkeypts, err_flags);
+                                                            (double)w_ot, flow, lists, lpos, parts, dkeypts, err_flags);
   EQD_CUDA_LAUNCH_CHECK();
   eqd::loss_total_kernel<<<1, 32, 0, st>>>(g->n_pairs, parts, (double)w_ot, (double)w_int, total);
   EQD_CUDA_LAUNCH_CHECK();

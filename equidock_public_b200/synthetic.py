@@ -63,3 +63,35 @@ def synthetic_batch(n_pairs: int, n_lig: int = 200, n_rec: int = 200, k: int = 1
 def to_torch_pairs(pairs):
     import torch
     return [tuple({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in d.items()} for d in p) for p in pairs]
+
+
+def synthetic_residue_protein(rng: np.random.Generator, n: int):
+    """All-atom stand-in of a protein for the GPU graph builder (graph_build.py): the same C-alpha random walk as
+    ``synthetic_protein``, backbone N / C atoms at 1.46 / 1.52 A with a ~110 degree N-CA-C angle, and 1..9 further atoms
+    within ~2.5 A of CA (side chain); residue types U{0..20}.  Returns the compact format of oracle/graph_oracle.py."""
+    steps = rng.normal(size=(n, 3))
+    steps /= np.linalg.norm(steps, axis=1, keepdims=True)
+    ca = (np.cumsum(steps * 3.8 * 0.35, axis=0) + rng.normal(scale=4.0, size=(n, 3))).astype(np.float32)
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    w = rng.normal(size=(n, 3)); w -= (w * u).sum(1, keepdims=True) * u; w /= np.linalg.norm(w, axis=1, keepdims=True)
+    ang = np.deg2rad(110.0)
+    n_at = ca + 1.46 * u
+    c_at = ca + 1.52 * (np.cos(ang) * u + np.sin(ang) * w)
+    n_side = rng.integers(1, 10, size=n)
+    atoms, ptr = [], [0]
+    for i in range(n):
+        side = ca[i] + rng.normal(scale=1.4, size=(n_side[i], 3))
+        a = np.concatenate([n_at[i:i + 1], ca[i:i + 1], c_at[i:i + 1], side]).astype(np.float32)
+        atoms.append(a)
+        ptr.append(ptr[-1] + a.shape[0])
+    return {'atoms': np.concatenate(atoms), 'atom_ptr': np.asarray(ptr, np.int32),
+            'nca_c': np.stack([n_at, ca, c_at], axis=1).astype(np.float32),
+            'res_feat': rng.integers(0, 21, size=(n, 1)).astype(np.float32)}
+
+
+def synthetic_residue_pair(rng: np.random.Generator, n_lig: int = 200, n_rec: int = 200):
+    lig, rec = synthetic_residue_protein(rng, n_lig), synthetic_residue_protein(rng, n_rec)
+    R, t = random_rigid(rng)
+    lig['atoms'] = ((R @ lig['atoms'].T).T + t).astype(np.float32)
+    lig['nca_c'] = ((lig['nca_c'].reshape(-1, 3) @ R.T) + t).astype(np.float32).reshape(-1, 3, 3)
+    return lig, rec

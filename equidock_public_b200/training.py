@@ -79,7 +79,7 @@ class LayerTrainPack:
     read, and the (source index, destination index) maps of every weight-gradient reduction (packed k-major partial ->
     flat state_dict-layout gradient)."""
 
-    def __init__(self, layer_module, packed: PackedLayer, layout: ParamLayout, device):
+    def __init__(self, layer_module, packed: PackedLayer, layout: ParamLayout, device, maps=None):
         dh, dhp = packed.dh, packed.dhp
         pw = 128 + 3 * dhp
         win = 2 * dhp + 64 + nat.H0_PAD
@@ -97,6 +97,9 @@ class LayerTrainPack:
                                'w2lin': sd['edge_mlp.4.weight'].contiguous(),
                                'w3lin': sd['coors_mlp.0.weight'].contiguous()}, device)
         self.dh, self.dhp, self.pw = dh, dhp, pw
+        if maps is not None:           # the index maps depend on the layout only: built once per module
+            self.maps = maps
+            return
         off = {n: layout.offset[id(p)] for n, p in layer_module.named_parameters()}
         ein = 2 * dh + 42
         w1n = 2 * dh + 64 + nat.H0            # node_mlp.0 input width
@@ -187,6 +190,7 @@ class TrainEngine:
         self.lib = nat.load()
         self.layout = ParamLayout(model)
         self._packs: Dict[int, tuple] = {}
+        self._maps: Dict[int, dict] = {}
         self._ws: Optional[BackwardWorkspace] = None
         self._head_maps = None
 
@@ -195,7 +199,10 @@ class TrainEngine:
         packed = lay_module.packed(self.device)
         hit = self._packs.get(id(lay_module))
         if hit is None or hit[0] is not packed:
-            hit = (packed, LayerTrainPack(lay_module, packed, self.layout, self.device))
+            maps = self._maps.get(id(lay_module))
+            tp = LayerTrainPack(lay_module, packed, self.layout, self.device, maps)
+            self._maps[id(lay_module)] = tp.maps
+            hit = (packed, tp)
             self._packs[id(lay_module)] = hit
         return hit[1]
 

@@ -385,6 +385,22 @@ int eqd_losses(const eqd_graph* g, const float* pred_lig /*[N_l][3]*/, const flo
                double* parts /*[B][4] mse, ot, intersection, -*/, double* total /*[4] loss, mse, ot, intersection*/,
                float* dcoors /*[N_l][3]*/, double* dkeypts /*[2B][50][3]*/, int32_t* err_flags, void* stream);
 
+/* ---- residue k-NN graph construction on the device (src/utils/protein_utils.py:212-397, RBFs :71-86) ------------------
+ * Proteins of a batch in engine order (ligand proteins of all pairs, then receptor proteins): seg_ptr [n_prot+1] residue
+ * offsets, atom_ptr [n+1] atom offsets per residue, atoms [A][3] fp32 (all atoms, residue by residue), nca_c [n][3][3]
+ * fp32 (N, CA, C of every residue), bound_ca [n][3] (bound-structure C-alpha trace the unbound one is aligned to; = CA
+ * at inference).  Stage 1 writes deg [n], x [n][3] (ndata['x']), mu_r_norm [n][5]; the caller forms row_ptr = exclusive
+ * prefix sum of deg (an index op) and calls stage 2, which writes col_src / edge_dst [E] (global node ids, grouped by
+ * destination) and he [E][27].  `workspace` (eqd_graph_build_workspace_bytes) carries the fp64 aligned coordinates, local
+ * frames and neighbour lists from stage 1 to stage 2.  max_neighbor <= 16.                                           */
+size_t eqd_graph_build_workspace_bytes(int32_t n_nodes);
+int eqd_graph_build_knn(int32_t n_prot, int32_t n_nodes, int32_t max_protein_nodes, const int32_t* seg_ptr,
+                        const int32_t* atom_ptr, const float* atoms, const float* nca_c, const float* bound_ca, float cutoff,
+                        int32_t max_neighbor, void* workspace, size_t workspace_bytes, int32_t* deg, float* x,
+                        float* mu_r_norm, void* stream);
+int eqd_graph_build_edges(int32_t n_nodes, const int32_t* row_ptr, const int32_t* deg, const void* workspace,
+                          int32_t* col_src, int32_t* edge_dst, float* he, void* stream);
+
 /* ---- batched RMSD meter (Meter_Unbound_Bound.update_rmsd, src/utils/eval.py:19-42; Kabsch src/utils/protein_utils.py:31-64) ----
  * out[b] = {complex RMSD after superimposing the predicted complex on the true one, ligand RMSD, receptor RMSD}, fp64.
  * Coordinates fp32, ligand arrays [N_l][3], receptor arrays [N_r][3] (receptor-local node order), batch order.        */

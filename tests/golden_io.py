@@ -68,3 +68,30 @@ def build_model(ds, device, sd=None, args=None):
     sd = sd if sd is not None else load_checkpoint(ds)
     model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
     return model.to(device).eval()
+
+
+_ALL = {}
+
+
+def load_all(ds):
+    """Compact fixtures of ALL shipped test pairs of a set (tests/golden/{ds}_all.npz, oracle/make_golden_all.py):
+    -> (names, {name: {'lig': protein, 'rec': protein, 'ref64': {...}, 'ref32': {...}, 'pdb': {...}, 'ca': {...}, 'yard': float}})
+    where protein = {'atoms', 'atom_ptr', 'nca_c', 'res_feat'} (the format of oracle/graph_oracle.py)."""
+    if ds in _ALL:
+        return _ALL[ds]
+    z = np.load(os.path.join(GOLDEN, f'{ds}_all.npz'))
+    names = [str(n) for n in z['names']]
+    out = {}
+    for n in names:
+        e = {}
+        for side in ('lig', 'rec'):
+            e[side] = {'atoms': z[f'{n}/{side}/atoms'], 'atom_ptr': z[f'{n}/{side}/atom_ptr'], 'nca_c': z[f'{n}/{side}/nca_c'],
+                       'res_feat': z[f'{n}/{side}/res_feat'].astype(np.float32).reshape(-1, 1)}
+            e[side]['bound_ca'] = e[side]['nca_c'][:, 1].copy()
+        for tag in ('ref64', 'ref32', 'pdb'):
+            e[tag] = {'rotation': z[f'{n}/{tag}/rotation'], 'translation': z[f'{n}/{tag}/translation']}
+        e['ca'] = {k: z[f'{n}/ca/{k}'] for k in ('ligand_in', 'ligand_gt', 'receptor_gt')}
+        e['yard'] = float(z[f'{n}/yard'])
+        out[n] = e
+    _ALL[ds] = (names, out)
+    return _ALL[ds]
