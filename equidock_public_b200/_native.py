@@ -86,7 +86,7 @@ PROTOTYPES = {
     'eqd_bwd_head_workspace_bytes': (C.c_size_t, [_i32, _i32, _i32]),
     'eqd_bwd_head': (C.c_int, [_G, _H] + [_vp] * 9 + [C.c_size_t] + [_vp] * 6),
     'eqd_losses_workspace_bytes': (C.c_size_t, [_i32, _i32]),
-    'eqd_losses': (C.c_int, [_G] + [_vp] * 7 + [_i32, _f32, _f32, _f32, _f32, _vp, C.c_size_t] + [_vp] * 6),
+    'eqd_losses': (C.c_int, [_G] + [_vp] * 7 + [_i32, _i32, _f32, _f32, _f32, _f32, _vp, C.c_size_t] + [_vp] * 6),
     'eqd_graph_build_workspace_bytes': (C.c_size_t, [_i32]),
     'eqd_graph_build_knn': (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
     'eqd_graph_build_edges': (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -88,23 +88,55 @@ loss_mse_intersection_kernel(eqd_graph g, const float* __restrict__ pred, const 
   }
 }
 
-struct OtSmem {
-  double P[OT_MAX_POCKET * 6];      // pocket points: ligand xyz, receptor xyz
-  double Y[EQD_HEADS * 6];          // keypoints: ligand xyz, receptor xyz
-  double u[OT_MAX_POCKET], ds[OT_MAX_POCKET];
-  double v[EQD_HEADS], dk[EQD_HEADS];
-  int excess[OT_MAX_POCKET], par_s[OT_MAX_POCKET];
-  int exl[OT_MAX_POCKET], expos[OT_MAX_POCKET];   // compact list of the sources that still have excess, and its inverse
-  int act[OT_MAX_POCKET];                          // sources reached by the sink settled last
-  int deficit[EQD_HEADS], par_k[EQD_HEADS], fl_cnt[EQD_HEADS];
-  unsigned char vis_s[OT_MAX_POCKET], vis_k[EQD_HEADS + 14];
-  double red_v[LOSS_THREADS];
-  int red_i[LOSS_THREADS];
-  int ctl[8];                                      // 0 mass left, 1 |exl|, 2 |act|, 3 settled node, 4 target
-  double ctl_d[2];
+// Per-CTA state of the transport solver, carved from dynamic shared memory for a pocket capacity `cap` (the largest pocket
+// of the batch): everything the serial parts of the algorithm touch lives on the SM.  FLOW_SMEM: the integer flows x and
+// the per-sink source lists are int16 arrays in shared memory too (cap <= OT_SMEM_CAP); otherwise int32 in global memory.
+#define OT_SMEM_CAP 704
+struct OtView {
+  double *P, *Y, *u, *ds, *v, *dk, *red_v, *ctl_d;
+  int *excess, *par_s, *exl, *expos, *act, *deficit, *par_k, *fl_cnt, *red_i, *ctl;
+  unsigned char *vis_s, *vis_k;
+  short *xs, *fls;
 };
+__host__ __device__ inline size_t ot_smem_bytes(int cap, bool flow_smem) {
+  size_t b = (size_t)(cap * 6 + EQD_HEADS * 6 + 2 * cap + 2 * EQD_HEADS + LOSS_THREADS + 2) * 8;
+  b += (size_t)(5 * cap + 3 * EQD_HEADS + LOSS_THREADS + 8) * 4;
+  b += (size_t)((cap + 64 + 15) & ~15);
+  if (flow_smem) b += (size_t)2 * cap * EQD_HEADS * 2;
+  return b + 64;
+}
+__device__ inline OtView ot_carve(unsigned char* base, int cap, bool flow_smem) {
+  OtView s;
+  double* d = reinterpret_cast<double*>(base);
+  s.P = d; d += cap * 6;
+  s.Y = d; d += EQD_HEADS * 6;
+  s.u = d; d += cap;
+  s.ds = d; d += cap;
+  s.v = d; d += EQD_HEADS;
+  s.dk = d; d += EQD_HEADS;
+  s.red_v = d; d += LOSS_THREADS;
+  s.ctl_d = d; d += 2;
+  int* i = reinterpret_cast<int*>(d);
+  s.excess = i; i += cap;
+  s.par_s = i; i += cap;
+  s.exl = i; i += cap;
+  s.expos = i; i += cap;
+  s.act = i; i += cap;
+  s.deficit = i; i += EQD_HEADS;
+  s.par_k = i; i += EQD_HEADS;
+  s.fl_cnt = i; i += EQD_HEADS;
+  s.red_i = i; i += LOSS_THREADS;
+  s.ctl = i; i += 8;
+  unsigned char* c = reinterpret_cast<unsigned char*>(i);
+  s.vis_s = c; c += cap;
+  s.vis_k = c; c += 64;
+  c = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(c) + 15) & ~(uintptr_t)15);
+  s.xs = reinterpret_cast<short*>(c);
+  s.fls = s.xs + (flow_smem ? (size_t)cap * EQD_HEADS : 0);
+  return s;
+}
 
-__device__ __forceinline__ double ot_cost(const OtSmem& s, int i, int k) {
+__device__ __forceinline__ double ot_cost(const OtView& s, int i, int k) {
   const double* p = s.P + i * 6;
   const double* y = s.Y + k * 6;
   double c = 0.0;
@@ -122,21 +154,22 @@ __device__ __forceinline__ double ot_cost(const OtSmem& s, int i, int k) {
 // Dijkstra only ever has to SETTLE SINKS (<= 50 pops per augmentation): settling sink k reaches the sources feeding it
 // (kept as a per-sink list, maintained by the augmenting thread), and those relax the other sinks.  All minima are
 // taken lexicographically over (value, index), so the result does not depend on list or thread order.
-// flow[(p0 + i) * 50 + k] (int32, global) = x_ik;  lists / pos: per-sink source lists and their inverse (global).
+// The final flows are written to flow[(p0 + i) * 50 + k] (int32, global).
+template <bool FLOW_SMEM>
 __global__ void __launch_bounds__(LOSS_THREADS)
-ot_emd_kernel(int n_pairs, const int* __restrict__ pocket_ptr, const float* __restrict__ pocket_lig,
+ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const float* __restrict__ pocket_lig,
               const float* __restrict__ pocket_rec, const double* __restrict__ keypts, double w_ot,
-              int* __restrict__ flow, int* __restrict__ lists, int* __restrict__ lpos, double* __restrict__ parts,
+              int* __restrict__ flow, int* __restrict__ lists, double* __restrict__ parts,
               double* __restrict__ dkeypts, int* __restrict__ err) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  OtSmem& s = *reinterpret_cast<OtSmem*>(smem_raw);
+  const OtView s = ot_carve(smem_raw, cap, FLOW_SMEM);
   const int b = blockIdx.x, tid = threadIdx.x, B = n_pairs;
   const int p0 = pocket_ptr[b], n = pocket_ptr[b + 1] - p0;
   constexpr int M = EQD_HEADS;
-  if (n <= 0 || n > OT_MAX_POCKET) {
+  if (n <= 0 || n > cap) {
     if (tid == 0) {
       parts[(long)b * 4 + 1] = 0.0;
-      if (n > OT_MAX_POCKET) atomicOr(err, 1);
+      if (n > cap) atomicOr(err, 1);
     }
     for (int o = tid; o < 2 * M * 3; o += LOSS_THREADS) {
       const int side = o / (M * 3), rem = o - side * M * 3;
@@ -154,10 +187,13 @@ ot_emd_kernel(int n_pairs, const int* __restrict__ pocket_ptr, const float* __re
     s.Y[k * 6 + c] = keypts[((long)b * M + k) * 3 + c];
     s.Y[k * 6 + 3 + c] = keypts[((long)(B + b) * M + k) * 3 + c];
   }
-  int* x = flow + (long)p0 * M;
-  int* fl = lists + (long)p0 * M;      // fl[k * n + idx]: sources with x_ik > 0
-  int* pos = lpos + (long)p0 * M;      // pos[i * M + k]: index of i in list k, or -1
-  for (int o = tid; o < n * M; o += LOSS_THREADS) { x[o] = 0; pos[o] = -1; }
+  int* xg = flow + (long)p0 * M;       // x_ik (global copy; the working copy when !FLOW_SMEM)
+  int* flg = lists + (long)p0 * M;     // fl[k * n + idx]: sources with x_ik > 0 (global when !FLOW_SMEM)
+  auto X = [&](int i, int k) -> int { return FLOW_SMEM ? (int)s.xs[i * M + k] : xg[(long)i * M + k]; };
+  auto setX = [&](int i, int k, int v) { if (FLOW_SMEM) s.xs[i * M + k] = (short)v; else xg[(long)i * M + k] = v; };
+  auto FL = [&](int k, int q) -> int { return FLOW_SMEM ? (int)s.fls[k * n + q] : flg[(long)k * n + q]; };
+  auto setFL = [&](int k, int q, int v) { if (FLOW_SMEM) s.fls[k * n + q] = (short)v; else flg[(long)k * n + q] = v; };
+  for (int o = tid; o < n * M; o += LOSS_THREADS) { if (FLOW_SMEM) s.xs[o] = 0; else xg[o] = 0; }
   __syncthreads();
   for (int i = tid; i < n; i += LOSS_THREADS) {     // u_i = min_k C_ik, v = 0: all reduced costs >= 0
     double mn = INFINITY;
@@ -227,7 +263,7 @@ ot_emd_kernel(int n_pairs, const int* __restrict__ pocket_ptr, const float* __re
       // settle sink k: the sources feeding it become reachable at the same distance (backward arcs cost 0)
       const int cnt = s.fl_cnt[k];
       for (int q = tid; q < cnt; q += LOSS_THREADS) {
-        const int i = fl[(long)k * n + q];
+        const int i = FL(k, q);
         if (!s.vis_s[i]) {
           s.vis_s[i] = 1;
           s.ds[i] = dist;
@@ -263,7 +299,7 @@ ot_emd_kernel(int n_pairs, const int* __restrict__ pocket_ptr, const float* __re
       while (true) {
         const int pk = s.par_s[i];
         if (pk < 0) { delta = min(delta, s.excess[i]); break; }
-        delta = min(delta, x[(long)i * M + pk]);
+        delta = min(delta, X(i, pk));
         k = pk;
         i = s.par_k[k];
         if (++hops > 2 * M + 2) { atomicOr(err, 4); delta = 0; break; }
@@ -273,13 +309,9 @@ ot_emd_kernel(int n_pairs, const int* __restrict__ pocket_ptr, const float* __re
         i = s.par_k[k];
         s.deficit[target] -= delta;
         while (true) {
-          int& xf = x[(long)i * M + k];
-          if (xf == 0) {                             // i starts feeding k
-            const int c = s.fl_cnt[k]++;
-            fl[(long)k * n + c] = i;
-            pos[(long)i * M + k] = c;
-          }
-          xf += delta;
+          const int xf = X(i, k);
+          if (xf == 0) setFL(k, s.fl_cnt[k]++, i);   // i starts feeding k
+          setX(i, k, xf + delta);
           const int pk = s.par_s[i];
           if (pk < 0) {
             s.excess[i] -= delta;
@@ -291,14 +323,13 @@ ot_emd_kernel(int n_pairs, const int* __restrict__ pocket_ptr, const float* __re
             }
             break;
           }
-          int& xb = x[(long)i * M + pk];
-          xb -= delta;
-          if (xb == 0) {                             // i stops feeding pk
-            const int q = pos[(long)i * M + pk], c = --s.fl_cnt[pk];
-            const int last = fl[(long)pk * n + c];
-            fl[(long)pk * n + q] = last;
-            pos[(long)last * M + pk] = q;
-            pos[(long)i * M + pk] = -1;
+          const int xb = X(i, pk) - delta;
+          setX(i, pk, xb);
+          if (xb == 0) {                             // i stops feeding pk: swap-remove it from pk's list
+            const int c = --s.fl_cnt[pk];
+            int q = 0;
+            while (q < c && FL(pk, q) != i) ++q;
+            setFL(pk, q, FL(pk, c));
           }
           k = pk;
           i = s.par_k[k];
@@ -319,7 +350,8 @@ ot_emd_kernel(int n_pairs, const int* __restrict__ pocket_ptr, const float* __re
   double tot = 0.0;
   for (int o = tid; o < n * M; o += LOSS_THREADS) {
     const int i = o / M, k = o - i * M;
-    const int f = x[o];
+    const int f = X(i, k);
+    if (FLOW_SMEM) xg[o] = f;                        // publish the plan
     if (f) tot += (double)f * ot_cost(s, i, k);
   }
   tot = block_sum_d(tot, s.red_v) * unit;
@@ -329,7 +361,7 @@ ot_emd_kernel(int n_pairs, const int* __restrict__ pocket_ptr, const float* __re
     const int k = o / 6, q = o - k * 6;
     double t = 0.0;
     for (int i = 0; i < n; ++i) {
-      const int f = x[(long)i * M + k];
+      const int f = X(i, k);
       if (f) t += (double)f * (s.Y[k * 6 + q] - s.P[i * 6 + q]);
     }
     const int side = q / 3, c = q - side * 3;
@@ -354,7 +386,7 @@ __global__ void loss_total_kernel(int n_pairs, const double* __restrict__ parts,
 extern "C" size_t eqd_losses_workspace_bytes(int32_t n_rec_nodes, int32_t n_pocket_total) {
   const size_t a = ((size_t)(n_rec_nodes > 0 ? n_rec_nodes : 1) * 8 + 255) & ~(size_t)255;
   const size_t f = ((size_t)(n_pocket_total > 0 ? n_pocket_total : 1) * EQD_HEADS * 4 + 255) & ~(size_t)255;
-  return a + 3 * f + 256;      // flows, per-sink source lists, list positions
+  return a + 2 * f + 256;      // flows, per-sink source lists
 }
 
 // parts[B][4] = {mse, ot, intersection, -} per pair; total[4] = {loss, mean mse, mean ot, mean intersection};
@@ -363,7 +395,7 @@ extern "C" size_t eqd_losses_workspace_bytes(int32_t n_rec_nodes, int32_t n_pock
 // failure.
 extern "C" int eqd_losses(const eqd_graph* g, const float* pred_lig, const float* bound_lig, const float* bound_rec,
                           const double* keypts, const int32_t* pocket_ptr, const float* pocket_lig,
-                          const float* pocket_rec, int32_t n_pocket_total, float w_ot, float w_int, float sigma,
+                          const float* pocket_rec, int32_t n_pocket_total, int32_t max_pocket, float w_ot, float w_int, float sigma,
                           float surface_ct, void* workspace, size_t workspace_bytes, double* parts, double* total,
                           float* dcoors, double* dkeypts, int32_t* err_flags, void* stream) {
   if (!g || !pred_lig || !bound_lig || !bound_rec || !keypts || !pocket_ptr || !pocket_lig || !pocket_rec || !workspace ||
@@ -378,17 +410,26 @@ extern "C" int eqd_losses(const eqd_graph* g, const float* pred_lig, const float
   const size_t fbytes = ((size_t)(n_pocket_total > 0 ? n_pocket_total : 1) * EQD_HEADS * 4 + 255) & ~(size_t)255;
   int* flow = reinterpret_cast<int*>(w + (((size_t)(n_rec > 0 ? n_rec : 1) * 8 + 255) & ~(size_t)255));
   int* lists = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(flow) + fbytes);
-  int* lpos = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(lists) + fbytes);
+
   cudaError_t me = cudaMemsetAsync(err_flags, 0, sizeof(int32_t), st);
   if (me != cudaSuccess) return -(1000 + (int)me);
   eqd::loss_mse_intersection_kernel<<<g->n_pairs, LOSS_THREADS, 0, st>>>(*g, pred_lig, bound_lig, bound_rec, (double)sigma,
                                                                         (double)surface_ct, (double)w_int, wrec, parts,
                                                                         dcoors);
   EQD_CUDA_LAUNCH_CHECK();
-  size_t smem = sizeof(eqd::OtSmem);
-  EQD_SET_SMEM((eqd::ot_emd_kernel), smem);
-  eqd::ot_emd_kernel<<<g->n_pairs, LOSS_THREADS, smem, st>>>(g->n_pairs, pocket_ptr, pocket_lig, pocket_rec, keypts,
-                                                            (double)w_ot, flow, lists, lpos, parts, dkeypts, err_flags);
+  int cap = max_pocket > 0 ? max_pocket : 1;
+  if (cap > OT_MAX_POCKET) cap = OT_MAX_POCKET;            // larger pockets are flagged by the kernel (err bit 1)
+  if (cap <= OT_SMEM_CAP) {
+    const size_t smem = eqd::ot_smem_bytes(cap, true);
+    EQD_SET_SMEM((eqd::ot_emd_kernel<true>), smem);
+    eqd::ot_emd_kernel<true><<<g->n_pairs, LOSS_THREADS, smem, st>>>(g->n_pairs, cap, pocket_ptr, pocket_lig, pocket_rec, keypts,
+                                                                    (double)w_ot, flow, lists, parts, dkeypts, err_flags);
+  } else {
+    const size_t smem = eqd::ot_smem_bytes(cap, false);
+    EQD_SET_SMEM((eqd::ot_emd_kernel<false>), smem);
+    eqd::ot_emd_kernel<false><<<g->n_pairs, LOSS_THREADS, smem, st>>>(g->n_pairs, cap, pocket_ptr, pocket_lig, pocket_rec, keypts,
+                                                                     (double)w_ot, flow, lists, parts, dkeypts, err_flags);
+  }
   EQD_CUDA_LAUNCH_CHECK();
   eqd::loss_total_kernel<<<1, 32, 0, st>>>(g->n_pairs, parts, (double)w_ot, (double)w_int, total);
   EQD_CUDA_LAUNCH_CHECK();

@@ -53,6 +53,12 @@ class ResidueBatch:
         return int(sum(v.numel() * v.element_size() for v in self.t.values()))
 
 
+def _edge_counts(ne_l, ne_r, B):
+    from .hetero_graph import CROSS_LR, CROSS_RL
+    z = torch.zeros(B, dtype=torch.int64)
+    return {LL: torch.tensor(ne_l, dtype=torch.int64), RR: torch.tensor(ne_r, dtype=torch.int64), CROSS_RL: z, CROSS_LR: z.clone()}
+
+
 class GraphBuffers:
     """Static device buffers of one graph build (inputs and outputs), so that a same-shaped batch can be rebuilt in place
     -- every pointer the forward's GraphPlan holds stays valid, which is what a CUDA-graph capture of
@@ -127,14 +133,18 @@ def build_graphs(rb: ResidueBatch, device, cutoff: float = 30.0, max_neighbor: i
         torch.cumsum(deg, 0, dtype=torch.int32, out=row_ptr[1:])    # exclusive prefix sum: an index op
         nat.check(lib.eqd_graph_build_edges(N, nat.ptr(row_ptr), nat.ptr(deg), nat.ptr(ws), nat.ptr(col_src), nat.ptr(edge_dst),
                                             nat.ptr(he), st), 'eqd_graph_build_edges')
-        if sync_sizes:
-            E_l, E = int(row_ptr[N_l].item()), int(row_ptr[N].item())
+        if sync_sizes:       # ONE small D2H: the edge offsets at the 2B + 1 protein boundaries
+            bounds = row_ptr[d['seg_ptr'].long()].cpu().tolist()
+            E_l, E = int(bounds[B]), int(bounds[2 * B])
+            ne_l = [bounds[i + 1] - bounds[i] for i in range(B)]
+            ne_r = [bounds[B + i + 1] - bounds[B + i] for i in range(B)]
         else:
             E_l = E = e_cap
+            ne_l = ne_r = None
     g = PairGraphBatch({LIGAND: N_l, RECEPTOR: N - N_l},
                        {LL: (col_src[:E_l], edge_dst[:E_l]), RR: (col_src[E_l:E] - N_l, edge_dst[E_l:E] - N_l)} if sync_sizes else {},
                        {LIGAND: torch.tensor(rb.n_lig, dtype=torch.int64), RECEPTOR: torch.tensor(rb.n_rec, dtype=torch.int64)},
-                       None)
+                       _edge_counts(ne_l, ne_r, B) if sync_sizes else None)
     g._ndata[LIGAND] = {'res_feat': d['res_feat'][:N_l], 'x': x[:N_l], 'new_x': x[:N_l], 'mu_r_norm': mu[:N_l]}
     g._ndata[RECEPTOR] = {'res_feat': d['res_feat'][N_l:], 'x': x[N_l:], 'mu_r_norm': mu[N_l:]}
     if sync_sizes:

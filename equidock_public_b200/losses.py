@@ -26,6 +26,7 @@ class PocketBatch:
         for s in sizes:
             ptr.append(ptr[-1] + s)
         self.n_pocket_total = ptr[-1]
+        self.max_pocket = max(sizes) if sizes else 0
         self.pocket_ptr = torch.tensor(ptr, dtype=torch.int32, device=device)
 
 
@@ -50,7 +51,7 @@ def device_losses(plan, pred_lig: torch.Tensor, keypts: torch.Tensor, tgt: Pocke
         kp = keypts.detach().to(torch.float64).contiguous()
         nat.check(lib.eqd_losses(C.byref(plan.struct), nat.ptr(pred), nat.ptr(tgt.bound_lig), nat.ptr(tgt.bound_rec), nat.ptr(kp),
                                  nat.ptr(tgt.pocket_ptr), nat.ptr(tgt.pocket_lig), nat.ptr(tgt.pocket_rec), tgt.n_pocket_total,
-                                 float(pocket_ot_loss_weight), float(intersection_loss_weight), float(intersection_sigma),
+                                 tgt.max_pocket, float(pocket_ot_loss_weight), float(intersection_loss_weight), float(intersection_sigma),
                                  float(intersection_surface_ct), nat.ptr(ws), ws_bytes, nat.ptr(parts), nat.ptr(total),
                                  nat.ptr(dco), nat.ptr(dkp), nat.ptr(err), st), 'eqd_losses')
     return {'total': total, 'parts': parts, 'dcoors': dco, 'dkeypts': dkp, 'err': err, '_keep': (ws, pred, kp)}

@@ -380,7 +380,8 @@ size_t eqd_losses_workspace_bytes(int32_t n_rec_nodes, int32_t n_pocket_total);
 int eqd_losses(const eqd_graph* g, const float* pred_lig /*[N_l][3]*/, const float* bound_lig /*[N_l][3]*/,
                const float* bound_rec /*[N_r][3]*/, const double* keypts /*[2B][50][3]*/,
                const int32_t* pocket_ptr /*[B+1]*/, const float* pocket_lig, const float* pocket_rec /*[sum P][3]*/,
-               int32_t n_pocket_total, float pocket_ot_loss_weight, float intersection_loss_weight,
+               int32_t n_pocket_total, int32_t max_pocket /* largest pocket of the batch (host value; <= 1024) */,
+               float pocket_ot_loss_weight, float intersection_loss_weight,
                float intersection_sigma, float intersection_surface_ct, void* workspace, size_t workspace_bytes,
                double* parts /*[B][4] mse, ot, intersection, -*/, double* total /*[4] loss, mse, ot, intersection*/,
                float* dcoors /*[N_l][3]*/, double* dkeypts /*[2B][50][3]*/, int32_t* err_flags, void* stream);
