@@ -207,7 +207,9 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
   if (tid == 0) { s.ctl[0] = n * M; s.ctl[1] = n; }
   __syncthreads();
   const long max_aug = 64L * (n + M) + 1024;
+  long n_aug = 0, n_pop = 0;
   for (long it = 0; it < max_aug && s.ctl[0] > 0; ++it) {
+    ++n_aug;
     const int nex = s.ctl[1];
     for (int i = tid; i < n; i += LOSS_THREADS) {
       const bool ex = s.excess[i] > 0;
@@ -258,6 +260,7 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
       __syncthreads();
       const int k = s.ctl[3];
       const double dist = s.ctl_d[0];
+      ++n_pop;
       if (k >= M || !(dist < INFINITY)) break;       // no augmenting path (cannot happen while mass remains)
       if (s.deficit[k] > 0) { target = k; D = dist; break; }
       // settle sink k: the sources feeding it become reachable at the same distance (backward arcs cost 0)
@@ -355,7 +358,10 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
     if (f) tot += (double)f * ot_cost(s, i, k);
   }
   tot = block_sum_d(tot, s.red_v) * unit;
-  if (tid == 0) parts[(long)b * 4 + 1] = tot;
+  if (tid == 0) {
+    parts[(long)b * 4 + 1] = tot;
+    parts[(long)b * 4 + 3] = (double)n_aug + 1e-9 * (double)n_pop;     // solver statistics: augmentations + 1e-9 * sinks settled
+  }
   const double gsc = 2.0 * unit * w_ot / (double)B;
   for (int o = tid; o < M * 6; o += LOSS_THREADS) {
     const int k = o / 6, q = o - k * 6;

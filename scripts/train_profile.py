@@ -56,6 +56,10 @@ def main():
         eng.backward(fwd, res['dcoors'], res['dkeypts'], flat=tr.flat_g); sync(); t.append(time.perf_counter())
         tr.invalidate_packed(); t.append(time.perf_counter())
         t0 = time.perf_counter(); tr.step(g, tgt); sync(); whole = time.perf_counter() - t0
+        if rep == 0:
+            st = res['parts'][:, 3].cpu().numpy()
+            pk = [int(t_[2]['pocket_lig'].shape[0]) for t_ in triples]
+            print('EMD solver: (pocket, augmentations, sinks settled):', [(p_, int(v), int(round((v - int(v)) * 1e9))) for p_, v in zip(pk, st)])
         d = np.diff(t) * 1e3
         print(f'rep {rep}: forward {d[0]:.2f} ms | losses {d[1]:.2f} ms | backward {d[2]:.2f} ms | invalidate {d[3]:.2f} ms | whole step {whole * 1e3:.2f} ms')
 
