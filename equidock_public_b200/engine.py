@@ -168,9 +168,21 @@ class PackedLayer:
 
 
 class PackedHead:
+    """Head parameters for the kernels.  mlp_h_mean_ROT's weight is needed k-major (transposed, 64 x 64: one tiny copy); the
+    3200 x 64 key / query projections and the bias are used IN PLACE when they already are fp32, contiguous, 16-byte
+    aligned device tensors (the normal case: no 1.6 MB round trip through the host per parameter version), else
+    through one host-packed upload."""
+
     def __init__(self, w_mean, b_mean, w_key, w_query, device, leaky_slope: float):
-        self.t = _upload_blob({'w_mean': _host_f32(w_mean).t().contiguous(), 'b_mean': _host_f32(b_mean),
-                               'w_key': _host_f32(w_key), 'w_query': _host_f32(w_query)}, device)
+        dev = torch.device(device)
+        inplace = all(t.is_cuda and t.device == dev and t.dtype == torch.float32 and t.is_contiguous() and t.data_ptr() % 16 == 0
+                      for t in (b_mean, w_key, w_query)) and w_mean.is_cuda
+        if inplace:
+            self.t = {'w_mean': w_mean.detach().to(torch.float32).t().contiguous(), 'b_mean': b_mean.detach(),
+                      'w_key': w_key.detach(), 'w_query': w_query.detach()}
+        else:
+            self.t = _upload_blob({'w_mean': _host_f32(w_mean).t().contiguous(), 'b_mean': _host_f32(b_mean),
+                                   'w_key': _host_f32(w_key), 'w_query': _host_f32(w_query)}, device)
         assert self.t['w_key'].shape == (nat.HEADS * nat.HID, nat.HID)
         s = nat.EqdHeadParams()
         for k, v in self.t.items():
@@ -178,7 +190,7 @@ class PackedHead:
                 setattr(s, k, v.data_ptr())
         s.leaky_slope = leaky_slope
         self.struct = s
-        # weights-only fold of the 50-head key / query projections (eqd_head_fold), done once per model on the device
+        # weights-only fold of the 50-head key / query projections (eqd_head_fold), done once per parameter version on the device
         self.m_qk = torch.empty(nat.HEADS, nat.HID, nat.HID, dtype=torch.float64, device=device)
         with torch.cuda.device(device):
             nat.check(nat.load().eqd_head_fold(C.byref(s), self.m_qk.data_ptr(), torch.cuda.current_stream().cuda_stream),
