@@ -91,16 +91,16 @@ loss_mse_intersection_kernel(eqd_graph g, const float* __restrict__ pred, const 
 // Per-CTA state of the transport solver, carved from dynamic shared memory for a pocket capacity `cap` (the largest pocket
 // of the batch): everything the serial parts of the algorithm touch lives on the SM.  FLOW_SMEM: the integer flows x and
 // the per-sink source lists are int16 arrays in shared memory too (cap <= OT_SMEM_CAP); otherwise int32 in global memory.
-#define OT_SMEM_CAP 704
+#define OT_SMEM_CAP 672
 struct OtView {
   double *P, *Y, *u, *ds, *v, *dk, *red_v, *ctl_d;
-  int *excess, *par_s, *exl, *expos, *act, *deficit, *par_k, *fl_cnt, *red_i, *ctl;
+  int *excess, *par_s, *exl, *expos, *act, *exq, *vislist, *deficit, *par_k, *fl_cnt, *red_i, *ctl;
   unsigned char *vis_s, *vis_k;
   short *xs, *fls;
 };
 __host__ __device__ inline size_t ot_smem_bytes(int cap, bool flow_smem) {
   size_t b = (size_t)(cap * 6 + EQD_HEADS * 6 + 2 * cap + 2 * EQD_HEADS + LOSS_THREADS + 2) * 8;
-  b += (size_t)(5 * cap + 3 * EQD_HEADS + LOSS_THREADS + 8) * 4;
+  b += (size_t)(7 * cap + 3 * EQD_HEADS + LOSS_THREADS + 8) * 4;
   b += (size_t)((cap + 64 + 15) & ~15);
   if (flow_smem) b += (size_t)2 * cap * EQD_HEADS * 2;
   return b + 64;
@@ -122,6 +122,8 @@ __device__ inline OtView ot_carve(unsigned char* base, int cap, bool flow_smem) 
   s.exl = i; i += cap;
   s.expos = i; i += cap;
   s.act = i; i += cap;
+  s.exq = i; i += cap;
+  s.vislist = i; i += cap;
   s.deficit = i; i += EQD_HEADS;
   s.par_k = i; i += EQD_HEADS;
   s.fl_cnt = i; i += EQD_HEADS;
@@ -194,159 +196,210 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
   auto FL = [&](int k, int q) -> int { return FLOW_SMEM ? (int)s.fls[k * n + q] : flg[(long)k * n + q]; };
   auto setFL = [&](int k, int q, int v) { if (FLOW_SMEM) s.fls[k * n + q] = (short)v; else flg[(long)k * n + q] = v; };
   for (int o = tid; o < n * M; o += LOSS_THREADS) { if (FLOW_SMEM) s.xs[o] = 0; else xg[o] = 0; }
-  __syncthreads();
-  for (int i = tid; i < n; i += LOSS_THREADS) {     // u_i = min_k C_ik, v = 0: all reduced costs >= 0
+  // u_i = min_k C_ik, v = 0: all reduced costs >= 0.  s.par_s doubles as the visit stamp store below (stamp in expos).
+  for (int i = tid; i < n; i += LOSS_THREADS) {
     double mn = INFINITY;
     for (int k = 0; k < M; ++k) mn = fmin(mn, ot_cost(s, i, k));
-    s.u[i] = mn;
+    s.u[i] = mn;                 // for a source WITH excess the true potential is u[i] + u_ex_off (lazy common shift)
     s.excess[i] = M;
     s.exl[i] = i;
-    s.expos[i] = i;
+    s.exq[i] = i;
+    s.act[i] = 0;
+    s.par_s[i] = -1;
+    s.vis_s[i] = 0;
   }
   if (tid < M) { s.v[tid] = 0.0; s.deficit[tid] = n; s.fl_cnt[tid] = 0; }
-  if (tid == 0) { s.ctl[0] = n * M; s.ctl[1] = n; }
   __syncthreads();
-  const long max_aug = 64L * (n + M) + 1024;
-  long n_aug = 0, n_pop = 0;
-  for (long it = 0; it < max_aug && s.ctl[0] > 0; ++it) {
-    ++n_aug;
-    const int nex = s.ctl[1];
-    for (int i = tid; i < n; i += LOSS_THREADS) {
-      const bool ex = s.excess[i] > 0;
-      s.ds[i] = ex ? 0.0 : INFINITY;
-      s.vis_s[i] = ex ? 1 : 0;
-      s.par_s[i] = -1;
-    }
-    // dk[k] = min over the sources with excess of the reduced cost: 2 threads per sink, merged lexicographically
-    {
-      const int k = tid & 63, part = tid >> 6;
-      double best = INFINITY;
-      int bi = 0x7fffffff;
-      if (k < M)
-        for (int q = part; q < nex; q += 2) {
-          const int i = s.exl[q];
-          const double rc = fmax(ot_cost(s, i, k) - s.u[i] - s.v[k], 0.0);
-          if (rc < best || (rc == best && i < bi)) { best = rc; bi = i; }
-        }
-      s.red_v[tid] = best;
-      s.red_i[tid] = bi;
-      __syncthreads();
-      if (tid < M) {
-        double o2 = s.red_v[tid + 64];
-        int i2 = s.red_i[tid + 64];
-        if (o2 < best || (o2 == best && i2 < bi)) { best = o2; bi = i2; }
-        s.dk[tid] = best;
-        s.par_k[tid] = bi;
-        s.vis_k[tid] = 0;
+  // base[k] = min over the sources with excess of (C_ik - u_i): changes only when a source leaves the excess set
+  // (stored in dk / par_k between augmentations' Dijkstra runs is not possible: kept in red_v / red_i[0..M))
+  {
+    const int k = tid & 63, part = tid >> 6;
+    double best = INFINITY;
+    int bi = 0x7fffffff;
+    if (k < M)
+      for (int q = part; q < n; q += 2) {
+        const double c = ot_cost(s, q, k) - s.u[q];
+        if (c < best || (c == best && q < bi)) { best = c; bi = q; }
       }
-      __syncthreads();
+    __shared__ double mv[LOSS_THREADS];
+    __shared__ int mi[LOSS_THREADS];
+    mv[tid] = best;
+    mi[tid] = bi;
+    __syncthreads();
+    if (tid < M) {
+      const double o2 = mv[tid + 64];
+      const int i2 = mi[tid + 64];
+      if (o2 < best || (o2 == best && i2 < bi)) { best = o2; bi = i2; }
+      s.red_v[tid] = best;         // base value
+      s.red_i[tid] = bi;           // base argmin
     }
-    int target = -1;
-    double D = 0.0;
-    for (int pop = 0; pop <= M; ++pop) {
-      if (tid < 32) {                                // warp 0: lexicographic argmin over the unsettled sinks
+    __syncthreads();
+  }
+  long n_aug = 0, n_pop = 0;
+  if (tid < 32) {
+    // ================= the whole primal-dual loop runs in warp 0: no block-wide barriers =================
+    const int lane = tid;
+    const int k0 = lane, k1 = lane + 32;               // the two sinks this lane owns (k1 valid iff < M)
+    const bool has1 = k1 < M;
+    int mass = n * M, nex = n, epoch = 0;
+    double u_ex_off = 0.0;
+    const long max_aug = 64L * (n + M) + 1024;
+    int fail = 0;
+    while (mass > 0 && n_aug < max_aug) {
+      ++n_aug;
+      ++epoch;
+      // tentative distances of my sinks from the sources with excess (all at distance 0)
+      double d0 = fmax(s.red_v[k0] - u_ex_off - s.v[k0], 0.0), d1 = has1 ? fmax(s.red_v[k1] - u_ex_off - s.v[k1], 0.0) : INFINITY;
+      int p0_ = s.red_i[k0], p1_ = has1 ? s.red_i[k1] : -1;
+      bool set0 = false, set1 = !has1;
+      int nvis = 0, target = -1;
+      double D = 0.0;
+      for (int pop = 0; pop <= M; ++pop) {
         double bv = INFINITY;
         int bk = 0x7fffffff;
-        for (int k = tid; k < M; k += 32)
-          if (!s.vis_k[k] && (s.dk[k] < bv || (s.dk[k] == bv && k < bk))) { bv = s.dk[k]; bk = k; }
+        if (!set0) { bv = d0; bk = k0; }
+        if (!set1 && (d1 < bv || (d1 == bv && k1 < bk))) { bv = d1; bk = k1; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
           const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
           if (ov < bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
         }
-        if (tid == 0) { s.ctl[3] = bk; s.ctl_d[0] = bv; s.ctl[2] = 0; }
-      }
-      __syncthreads();
-      const int k = s.ctl[3];
-      const double dist = s.ctl_d[0];
-      ++n_pop;
-      if (k >= M || !(dist < INFINITY)) break;       // no augmenting path (cannot happen while mass remains)
-      if (s.deficit[k] > 0) { target = k; D = dist; break; }
-      // settle sink k: the sources feeding it become reachable at the same distance (backward arcs cost 0)
-      const int cnt = s.fl_cnt[k];
-      for (int q = tid; q < cnt; q += LOSS_THREADS) {
-        const int i = FL(k, q);
-        if (!s.vis_s[i]) {
-          s.vis_s[i] = 1;
-          s.ds[i] = dist;
-          s.par_s[i] = k;
-          s.act[atomicAdd(&s.ctl[2], 1)] = i;
+        ++n_pop;
+        if (bk >= M || !(bv < INFINITY)) break;
+        if (s.deficit[bk] > 0) { target = bk; D = bv; break; }
+        if (bk == k0) set0 = true;
+        if (bk == k1) set1 = true;
+        // settle sink bk: the sources feeding it become reachable at distance bv (backward arcs cost 0)
+        const int cnt = s.fl_cnt[bk];
+        const int first_new = nvis;
+        for (int q0 = 0; q0 < cnt; q0 += 32) {
+          const int q = q0 + lane;
+          int i = -1;
+          bool ok = false;
+          if (q < cnt) {
+            i = FL(bk, q);
+            ok = s.excess[i] == 0 && s.act[i] != epoch;     // act[] = visit stamp of a source
+          }
+          const unsigned mk = __ballot_sync(0xffffffffu, ok);
+          if (ok) {
+            const int slot = nvis + __popc(mk & ((1u << lane) - 1u));
+            s.act[i] = epoch;
+            s.ds[i] = bv;
+            s.par_s[i] = bk;
+            s.vislist[slot] = i;
+          }
+          nvis += __popc(mk);
+        }
+        __syncwarp();
+        // relax my unsettled sinks through the newly reached sources
+        for (int q = first_new; q < nvis; ++q) {
+          const int i = s.vislist[q];
+          const double ui = s.u[i];
+          if (!set0) {
+            const double nd = bv + fmax(ot_cost(s, i, k0) - ui - s.v[k0], 0.0);
+            if (nd < d0 || (nd == d0 && i < p0_)) { d0 = nd; p0_ = i; }
+          }
+          if (!set1) {
+            const double nd = bv + fmax(ot_cost(s, i, k1) - ui - s.v[k1], 0.0);
+            if (nd < d1 || (nd == d1 && i < p1_)) { d1 = nd; p1_ = i; }
+          }
         }
       }
-      if (tid == 0) s.vis_k[k] = 1;
-      __syncthreads();
-      const int nact = s.ctl[2];
-      if (tid < M && !s.vis_k[tid] && nact > 0) {    // relax the forward arcs of the newly reached sources
-        double best = s.dk[tid];
-        int bi = s.par_k[tid];
-        for (int q = 0; q < nact; ++q) {
-          const int i = s.act[q];
-          const double nd = dist + fmax(ot_cost(s, i, tid) - s.u[i] - s.v[tid], 0.0);
-          if (nd < best || (nd == best && i < bi)) { best = nd; bi = i; }
-        }
-        s.dk[tid] = best;
-        s.par_k[tid] = bi;
+      if (target < 0) { fail |= 2; break; }
+      // publish the parents of the settled sinks and of the target; potentials (common shifts dropped, see header):
+      // visited sources u += D - ds; sources with excess: lazy +D; settled sinks v -= D - dk
+      if (set0 || k0 == target) s.par_k[k0] = p0_;
+      if (has1 && (set1 || k1 == target)) s.par_k[k1] = p1_;
+      if (set0) s.v[k0] -= D - d0;
+      if (has1 && set1) s.v[k1] -= D - d1;
+      for (int q = lane; q < nvis; q += 32) {
+        const int i = s.vislist[q];
+        s.u[i] += D - s.ds[i];
       }
-      __syncthreads();
-    }
-    if (target < 0) { if (tid == 0) atomicOr(err, 2); break; }
-    // ---- potentials: u_i -= min(ds_i, D), v_k += min(dk_k, D) ----
-    for (int i = tid; i < n; i += LOSS_THREADS) s.u[i] -= fmin(s.ds[i], D);
-    if (tid < M) s.v[tid] += fmin(s.dk[tid], D);
-    __syncthreads();
-    // ---- augment along the parent chain and maintain the lists (one thread: deterministic) ----
-    if (tid == 0) {
-      int delta = s.deficit[target];
-      int k = target, i = s.par_k[k], hops = 0;
-      while (true) {
-        const int pk = s.par_s[i];
-        if (pk < 0) { delta = min(delta, s.excess[i]); break; }
-        delta = min(delta, X(i, pk));
-        k = pk;
-        i = s.par_k[k];
-        if (++hops > 2 * M + 2) { atomicOr(err, 4); delta = 0; break; }
-      }
-      if (delta > 0) {
-        k = target;
-        i = s.par_k[k];
-        s.deficit[target] -= delta;
+      u_ex_off += D;
+      __syncwarp();
+      // ---- augment along the parent chain and maintain the lists (lane 0) ----
+      int left = -1;                                   // a source that just lost its last unit of excess
+      if (lane == 0) {
+        int delta = s.deficit[target];
+        int k = target, i = s.par_k[k], hops = 0;
         while (true) {
-          const int xf = X(i, k);
-          if (xf == 0) setFL(k, s.fl_cnt[k]++, i);   // i starts feeding k
-          setX(i, k, xf + delta);
+          const bool mid = s.excess[i] == 0;           // reached through a backward arc
+          if (!mid) { delta = min(delta, s.excess[i]); break; }
           const int pk = s.par_s[i];
-          if (pk < 0) {
-            s.excess[i] -= delta;
-            if (s.excess[i] == 0) {                  // drop i from the excess list (swap with the last entry)
-              const int q = s.expos[i], last = s.exl[s.ctl[1] - 1];
-              s.exl[q] = last;
-              s.expos[last] = q;
-              s.ctl[1] -= 1;
-            }
-            break;
-          }
-          const int xb = X(i, pk) - delta;
-          setX(i, pk, xb);
-          if (xb == 0) {                             // i stops feeding pk: swap-remove it from pk's list
-            const int c = --s.fl_cnt[pk];
-            int q = 0;
-            while (q < c && FL(pk, q) != i) ++q;
-            setFL(pk, q, FL(pk, c));
-          }
+          delta = min(delta, X(i, pk));
           k = pk;
           i = s.par_k[k];
+          if (++hops > 2 * M + 2) { fail |= 4; delta = 0; break; }
         }
-        s.ctl[0] -= delta;
-      } else {
-        atomicOr(err, 8);
-        s.ctl[0] = 0;
+        if (delta > 0) {
+          k = target;
+          i = s.par_k[k];
+          s.deficit[target] -= delta;
+          while (true) {
+            const int xf = X(i, k);
+            if (xf == 0) setFL(k, s.fl_cnt[k]++, i);   // i starts feeding k
+            setX(i, k, xf + delta);
+            if (s.excess[i] > 0) {
+              s.excess[i] -= delta;
+              if (s.excess[i] == 0) left = i;
+              break;
+            }
+            const int pk = s.par_s[i];
+            const int xb = X(i, pk) - delta;
+            setX(i, pk, xb);
+            if (xb == 0) {                             // i stops feeding pk: swap-remove it from pk's list
+              const int c = --s.fl_cnt[pk];
+              int q = 0;
+              while (q < c && FL(pk, q) != i) ++q;
+              setFL(pk, q, FL(pk, c));
+            }
+            k = pk;
+            i = s.par_k[k];
+          }
+          mass -= delta;
+        } else {
+          fail |= 8;
+          mass = 0;
+        }
       }
+      mass = __shfl_sync(0xffffffffu, mass, 0);
+      left = __shfl_sync(0xffffffffu, left, 0);
+      fail = __shfl_sync(0xffffffffu, fail, 0);
+      if (fail) break;
+      if (left >= 0) {
+        // the source leaves the excess set: materialise its potential, drop it from the list, and recompute the base of
+        // the sinks whose minimiser it was
+        if (lane == 0) {
+          s.u[left] += u_ex_off;
+          const int q = s.exq[left], last = s.exl[nex - 1];
+          s.exl[q] = last;
+          s.exq[last] = q;
+        }
+        nex -= 1;
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int k = t == 0 ? k0 : k1;
+          if (k < M && s.red_i[k] == left) {
+            double best = INFINITY;
+            int bi = 0x7fffffff;
+            for (int q = 0; q < nex; ++q) {
+              const int i = s.exl[q];
+              const double c = ot_cost(s, i, k) - s.u[i];
+              if (c < best || (c == best && i < bi)) { best = c; bi = i; }
+            }
+            s.red_v[k] = best;
+            s.red_i[k] = bi;
+          }
+        }
+      }
+      __syncwarp();
     }
-    __threadfence_block();
-    __syncthreads();
+    if (mass > 0) fail |= 16;
+    if (lane == 0 && fail) atomicOr(err, fail);
   }
-  if (s.ctl[0] > 0 && tid == 0) atomicOr(err, 16);
   __syncthreads();
   // ---- value and keypoint gradients from the (constant) plan T = x / (n * M) ----
   const double unit = 1.0 / ((double)n * (double)M);

@@ -50,7 +50,13 @@ def test_gpu_built_graphs_equal_the_graph_oracle(ds, cuda_device):
                     sel2 = ref['dst'] == i
                     msg.append(f'oracle nbrs {ref["src"][sel2].tolist()} dist {ref["dist"][sel2].tolist()}')
                 raise AssertionError(' | '.join(msg))
-            assert np.abs(_np(part.edges[et].data['he']) - ref['he']).max() < 5e-6, (n, side)
+            he = _np(part.edges[et].data['he'])
+            assert np.abs(np.delete(he - ref['he'], [15, 16, 17], axis=1)).max() < 5e-6, (n, side)      # RBFs, q_ij, k_ij, t_ij
+            # p_ij = frame . (x_src - x_dst): the reference (and the oracle) align the C-alpha trace with a FLOAT32 Kabsch
+            # (protein_utils.py:284-291, R = I + ~6e-8 noise), which moves coordinates of magnitude |x| by ~1e-7 |x|; the
+            # device aligns in fp64 (R = I exactly at inference)
+            xmax = float(np.abs(ref['x']).max())
+            assert np.abs(he[:, 15:18] - ref['he'][:, 15:18]).max() < 5e-6 + 4e-7 * xmax, (n, side, xmax)
             assert np.abs(_np(part.nodes[nt].data['mu_r_norm']) - ref['mu_r_norm']).max() < 5e-6
             assert np.abs(_np(part.nodes[nt].data['x']) - ref['x']).max() < 1e-5
 
