@@ -89,23 +89,30 @@ loss_mse_intersection_kernel(eqd_graph g, const float* __restrict__ pred, const 
 }
 
 // Per-CTA state of the transport solver, carved from dynamic shared memory for a pocket capacity `cap` (the largest pocket
-// of the batch): everything the serial parts of the algorithm touch lives on the SM.  FLOW_SMEM: the integer flows x and
-// the per-sink source lists are int16 arrays in shared memory too (cap <= OT_SMEM_CAP); otherwise int32 in global memory.
-#define OT_SMEM_CAP 672
+// of the batch).  The cost matrix C (fp64, cap x 50) and the per-sink source lists (int16) live in shared memory when they
+// fit (cap <= 346: both; <= 410: C only; <= 917: lists only), else in global memory (L2); flows x_ik <= 50 are int8.
 struct OtView {
-  double *P, *Y, *u, *ds, *v, *dk, *red_v, *ctl_d;
-  int *excess, *par_s, *exl, *expos, *act, *exq, *vislist, *deficit, *par_k, *fl_cnt, *red_i, *ctl;
-  unsigned char *vis_s, *vis_k;
-  short *xs, *fls;
+  double *P, *Y, *u, *ds, *v, *base_v, *Cm;
+  int *excess, *par_s, *exl, *exq, *stamp, *vislist, *deficit, *par_k, *fl_cnt, *base_i;
+  signed char* xs;
+  short* fls;
 };
-__host__ __device__ inline size_t ot_smem_bytes(int cap, bool flow_smem) {
-  size_t b = (size_t)(cap * 6 + EQD_HEADS * 6 + 2 * cap + 2 * EQD_HEADS + LOSS_THREADS + 2) * 8;
-  b += (size_t)(7 * cap + 3 * EQD_HEADS + LOSS_THREADS + 8) * 4;
-  b += (size_t)((cap + 64 + 15) & ~15);
-  if (flow_smem) b += (size_t)2 * cap * EQD_HEADS * 2;
-  return b + 64;
+struct OtLayout {
+  size_t bytes;
+  int c_smem, fl_smem;
+};
+__host__ __device__ inline OtLayout ot_layout(int cap) {
+  const size_t fixed = (size_t)(cap * 6 + EQD_HEADS * 6 + 2 * cap + 2 * EQD_HEADS) * 8 + (size_t)(6 * cap + 4 * EQD_HEADS) * 4 +
+                       (size_t)cap * EQD_HEADS + 256;
+  const size_t cbytes = (size_t)cap * EQD_HEADS * 8, fbytes = (size_t)cap * EQD_HEADS * 2;
+  const size_t lim = 227 * 1024 - 2048;      // static shared memory of the kernel is ~1.5 KB
+  OtLayout L;
+  L.c_smem = fixed + cbytes <= lim;
+  L.fl_smem = fixed + (L.c_smem ? cbytes : 0) + fbytes <= lim;
+  L.bytes = fixed + (L.c_smem ? cbytes : 0) + (L.fl_smem ? fbytes : 0);
+  return L;
 }
-__device__ inline OtView ot_carve(unsigned char* base, int cap, bool flow_smem) {
+__device__ inline OtView ot_carve(unsigned char* base, int cap, const OtLayout& L, double* c_global, short* fl_global) {
   OtView s;
   double* d = reinterpret_cast<double*>(base);
   s.P = d; d += cap * 6;
@@ -113,61 +120,63 @@ __device__ inline OtView ot_carve(unsigned char* base, int cap, bool flow_smem) 
   s.u = d; d += cap;
   s.ds = d; d += cap;
   s.v = d; d += EQD_HEADS;
-  s.dk = d; d += EQD_HEADS;
-  s.red_v = d; d += LOSS_THREADS;
-  s.ctl_d = d; d += 2;
+  s.base_v = d; d += EQD_HEADS;
+  if (L.c_smem) { s.Cm = d; d += (size_t)cap * EQD_HEADS; } else s.Cm = c_global;
   int* i = reinterpret_cast<int*>(d);
   s.excess = i; i += cap;
   s.par_s = i; i += cap;
   s.exl = i; i += cap;
-  s.expos = i; i += cap;
-  s.act = i; i += cap;
   s.exq = i; i += cap;
+  s.stamp = i; i += cap;
   s.vislist = i; i += cap;
   s.deficit = i; i += EQD_HEADS;
   s.par_k = i; i += EQD_HEADS;
   s.fl_cnt = i; i += EQD_HEADS;
-  s.red_i = i; i += LOSS_THREADS;
-  s.ctl = i; i += 8;
-  unsigned char* c = reinterpret_cast<unsigned char*>(i);
-  s.vis_s = c; c += cap;
-  s.vis_k = c; c += 64;
-  c = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(c) + 15) & ~(uintptr_t)15);
-  s.xs = reinterpret_cast<short*>(c);
-  s.fls = s.xs + (flow_smem ? (size_t)cap * EQD_HEADS : 0);
+  s.base_i = i; i += EQD_HEADS;
+  short* h = reinterpret_cast<short*>(i);
+  if (L.fl_smem) { s.fls = h; h += (size_t)cap * EQD_HEADS; } else s.fls = fl_global;
+  s.xs = reinterpret_cast<signed char*>(h);
   return s;
 }
 
-__device__ __forceinline__ double ot_cost(const OtView& s, int i, int k) {
-  const double* p = s.P + i * 6;
-  const double* y = s.Y + k * 6;
-  double c = 0.0;
-#pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    const double d = p[q] - y[q];
-    c = fma(d, d, c);
-  }
-  return c;
+// lexicographic (value, index) minimum over the warp of non-negative doubles: the bit pattern of a non-negative double is
+// monotone as a 64-bit unsigned integer, so three 32-bit warp reductions replace five rounds of 64-bit shuffles
+__device__ __forceinline__ void warp_argmin(double& v, int& k) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+  const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+  const unsigned mk = __reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? (unsigned)k : 0xffffffffu);
+  v = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+  k = (int)mk;
 }
 
-// One CTA per pair: successive shortest augmenting paths with node potentials on the transport problem scaled to
-// integers (supply 50 per pocket point, demand n per keypoint, n * 50 units in all).  Because forward arcs form a
-// complete bipartite graph and backward arcs (k -> i, flow x_ik > 0) have reduced cost 0 by complementary slackness,
-// Dijkstra only ever has to SETTLE SINKS (<= 50 pops per augmentation): settling sink k reaches the sources feeding it
-// (kept as a per-sink list, maintained by the augmenting thread), and those relax the other sinks.  All minima are
-// taken lexicographically over (value, index), so the result does not depend on list or thread order.
+// One CTA per pair: successive shortest augmenting paths with node potentials on the transport problem scaled to integers
+// (supply 50 per pocket point, demand n per keypoint, n * 50 units in all); the whole primal-dual loop runs in warp 0.
+//   * Forward arcs form a complete bipartite graph and backward arcs (k -> i, x_ik > 0) have reduced cost 0 (complementary
+//     slackness), so Dijkstra only SETTLES SINKS: lane l owns sinks l and l + 32 (distances and parents in registers).
+//     All unsettled sinks at the current minimum distance are settled in one round (they are final: arc lengths >= 0;
+//     with potentials most of the search happens at distance 0); settling sink k reaches the sources feeding it (per-sink
+//     lists maintained by the augmenting lane), which relax the other sinks through the cached cost matrix.
+//   * Potentials are kept modulo the common shift of an augmentation (u += D everywhere, v -= D everywhere leaves every
+//     reduced cost unchanged): only visited sources (u += D - ds) and settled sinks (v -= D - dk) are touched; the sources
+//     that still have excess all sit at distance 0 and share ONE lazy offset, so their contribution to the initial sink
+//     distances, base[k] = min_i (C_ik - u_i), changes only when the minimiser leaves the excess set.
+//   * All minima are lexicographic in (value, index): the plan does not depend on list or lane order.
 // The final flows are written to flow[(p0 + i) * 50 + k] (int32, global).
-template <bool FLOW_SMEM>
 __global__ void __launch_bounds__(LOSS_THREADS)
 ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const float* __restrict__ pocket_lig,
               const float* __restrict__ pocket_rec, const double* __restrict__ keypts, double w_ot,
-              int* __restrict__ flow, int* __restrict__ lists, double* __restrict__ parts,
+              int* __restrict__ flow, short* __restrict__ lists_g, double* __restrict__ cost_g, double* __restrict__ parts,
               double* __restrict__ dkeypts, int* __restrict__ err) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const OtView s = ot_carve(smem_raw, cap, FLOW_SMEM);
   const int b = blockIdx.x, tid = threadIdx.x, B = n_pairs;
   const int p0 = pocket_ptr[b], n = pocket_ptr[b + 1] - p0;
   constexpr int M = EQD_HEADS;
+  const OtLayout L = ot_layout(cap);
+  const OtView s = ot_carve(smem_raw, cap, L, cost_g + (long)p0 * M, lists_g + (long)p0 * M);
+  __shared__ double red[LOSS_THREADS];
+  __shared__ int redi[LOSS_THREADS];
   if (n <= 0 || n > cap) {
     if (tid == 0) {
       parts[(long)b * 4 + 1] = 0.0;
@@ -189,130 +198,137 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
     s.Y[k * 6 + c] = keypts[((long)b * M + k) * 3 + c];
     s.Y[k * 6 + 3 + c] = keypts[((long)(B + b) * M + k) * 3 + c];
   }
-  int* xg = flow + (long)p0 * M;       // x_ik (global copy; the working copy when !FLOW_SMEM)
-  int* flg = lists + (long)p0 * M;     // fl[k * n + idx]: sources with x_ik > 0 (global when !FLOW_SMEM)
-  auto X = [&](int i, int k) -> int { return FLOW_SMEM ? (int)s.xs[i * M + k] : xg[(long)i * M + k]; };
-  auto setX = [&](int i, int k, int v) { if (FLOW_SMEM) s.xs[i * M + k] = (short)v; else xg[(long)i * M + k] = v; };
-  auto FL = [&](int k, int q) -> int { return FLOW_SMEM ? (int)s.fls[k * n + q] : flg[(long)k * n + q]; };
-  auto setFL = [&](int k, int q, int v) { if (FLOW_SMEM) s.fls[k * n + q] = (short)v; else flg[(long)k * n + q] = v; };
-  for (int o = tid; o < n * M; o += LOSS_THREADS) { if (FLOW_SMEM) s.xs[o] = 0; else xg[o] = 0; }
-  // u_i = min_k C_ik, v = 0: all reduced costs >= 0.  s.par_s doubles as the visit stamp store below (stamp in expos).
-  for (int i = tid; i < n; i += LOSS_THREADS) {
+  __syncthreads();
+  for (int o = tid; o < n * M; o += LOSS_THREADS) {      // cost matrix, once
+    const int i = o / M, k = o - i * M;
+    double c = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const double d = s.P[i * 6 + q] - s.Y[k * 6 + q];
+      c = fma(d, d, c);
+    }
+    s.Cm[o] = c;
+    s.xs[o] = 0;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += LOSS_THREADS) {          // u_i = min_k C_ik, v = 0: all reduced costs >= 0
     double mn = INFINITY;
-    for (int k = 0; k < M; ++k) mn = fmin(mn, ot_cost(s, i, k));
+    for (int k = 0; k < M; ++k) mn = fmin(mn, s.Cm[i * M + k]);
     s.u[i] = mn;                 // for a source WITH excess the true potential is u[i] + u_ex_off (lazy common shift)
     s.excess[i] = M;
     s.exl[i] = i;
     s.exq[i] = i;
-    s.act[i] = 0;
+    s.stamp[i] = 0;
     s.par_s[i] = -1;
-    s.vis_s[i] = 0;
   }
   if (tid < M) { s.v[tid] = 0.0; s.deficit[tid] = n; s.fl_cnt[tid] = 0; }
   __syncthreads();
-  // base[k] = min over the sources with excess of (C_ik - u_i): changes only when a source leaves the excess set
-  // (stored in dk / par_k between augmentations' Dijkstra runs is not possible: kept in red_v / red_i[0..M))
-  {
+  {   // base[k] = min over the sources with excess of (C_ik - u_i): two threads per sink, merged lexicographically
     const int k = tid & 63, part = tid >> 6;
     double best = INFINITY;
     int bi = 0x7fffffff;
     if (k < M)
       for (int q = part; q < n; q += 2) {
-        const double c = ot_cost(s, q, k) - s.u[q];
+        const double c = s.Cm[q * M + k] - s.u[q];
         if (c < best || (c == best && q < bi)) { best = c; bi = q; }
       }
-    __shared__ double mv[LOSS_THREADS];
-    __shared__ int mi[LOSS_THREADS];
-    mv[tid] = best;
-    mi[tid] = bi;
+    red[tid] = best;
+    redi[tid] = bi;
     __syncthreads();
     if (tid < M) {
-      const double o2 = mv[tid + 64];
-      const int i2 = mi[tid + 64];
+      const double o2 = red[tid + 64];
+      const int i2 = redi[tid + 64];
       if (o2 < best || (o2 == best && i2 < bi)) { best = o2; bi = i2; }
-      s.red_v[tid] = best;         // base value
-      s.red_i[tid] = bi;           // base argmin
+      s.base_v[tid] = best;
+      s.base_i[tid] = bi;
     }
     __syncthreads();
   }
   long n_aug = 0, n_pop = 0;
   if (tid < 32) {
-    // ================= the whole primal-dual loop runs in warp 0: no block-wide barriers =================
     const int lane = tid;
     const int k0 = lane, k1 = lane + 32;               // the two sinks this lane owns (k1 valid iff < M)
     const bool has1 = k1 < M;
-    int mass = n * M, nex = n, epoch = 0;
+    int mass = n * M, nex = n, epoch = 0, fail = 0;
     double u_ex_off = 0.0;
     const long max_aug = 64L * (n + M) + 1024;
-    int fail = 0;
+    auto X = [&](int i, int k) -> int { return (int)s.xs[i * M + k]; };
     while (mass > 0 && n_aug < max_aug) {
       ++n_aug;
       ++epoch;
-      // tentative distances of my sinks from the sources with excess (all at distance 0)
-      double d0 = fmax(s.red_v[k0] - u_ex_off - s.v[k0], 0.0), d1 = has1 ? fmax(s.red_v[k1] - u_ex_off - s.v[k1], 0.0) : INFINITY;
-      int p0_ = s.red_i[k0], p1_ = has1 ? s.red_i[k1] : -1;
+      // (+ 0.0 turns a -0.0 into +0.0: warp_argmin orders distances by their bit patterns)
+      double d0 = fmax(s.base_v[k0] - u_ex_off - s.v[k0], 0.0) + 0.0, d1 = has1 ? fmax(s.base_v[k1] - u_ex_off - s.v[k1], 0.0) + 0.0 : INFINITY;
+      int p0_ = s.base_i[k0], p1_ = has1 ? s.base_i[k1] : -1;
+      const double v0 = s.v[k0], v1 = has1 ? s.v[k1] : 0.0;
       bool set0 = false, set1 = !has1;
       int nvis = 0, target = -1;
       double D = 0.0;
-      for (int pop = 0; pop <= M; ++pop) {
+      for (int round = 0; round <= M; ++round) {
         double bv = INFINITY;
         int bk = 0x7fffffff;
         if (!set0) { bv = d0; bk = k0; }
         if (!set1 && (d1 < bv || (d1 == bv && k1 < bk))) { bv = d1; bk = k1; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-          const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-          if (ov < bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
-        }
+        warp_argmin(bv, bk);
         ++n_pop;
         if (bk >= M || !(bv < INFINITY)) break;
-        if (s.deficit[bk] > 0) { target = bk; D = bv; break; }
-        if (bk == k0) set0 = true;
-        if (bk == k1) set1 = true;
-        // settle sink bk: the sources feeding it become reachable at distance bv (backward arcs cost 0)
-        const int cnt = s.fl_cnt[bk];
+        // every unsettled sink at distance bv is final; a deficit among them ends the search (lowest index wins)
+        const bool at0 = !set0 && d0 == bv, at1 = !set1 && d1 == bv;
+        const unsigned m0 = __ballot_sync(0xffffffffu, at0), m1 = __ballot_sync(0xffffffffu, at1);
+        const unsigned t0 = __ballot_sync(0xffffffffu, at0 && s.deficit[k0] > 0);
+        const unsigned t1 = __ballot_sync(0xffffffffu, at1 && s.deficit[has1 ? k1 : 0] > 0);
+        if (t0 | t1) { target = t0 ? (__ffs(t0) - 1) : (32 + __ffs(t1) - 1); D = bv; break; }
+        if (at0) set0 = true;
+        if (at1) set1 = true;
         const int first_new = nvis;
-        for (int q0 = 0; q0 < cnt; q0 += 32) {
-          const int q = q0 + lane;
-          int i = -1;
-          bool ok = false;
-          if (q < cnt) {
-            i = FL(bk, q);
-            ok = s.excess[i] == 0 && s.act[i] != epoch;     // act[] = visit stamp of a source
+        // settle them in ascending sink order: the sources feeding a sink become reachable at distance bv
+        for (int half = 0; half < 2; ++half) {
+          unsigned mm = half == 0 ? m0 : m1;
+          while (mm) {
+            const int bit = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const int ks = half * 32 + bit;
+            const int cnt = s.fl_cnt[ks];
+            for (int q0 = 0; q0 < cnt; q0 += 32) {
+              const int q = q0 + lane;
+              int i = -1;
+              bool ok = false;
+              if (q < cnt) {
+                i = (int)s.fls[ks * n + q];
+                ok = s.excess[i] == 0 && s.stamp[i] != epoch;
+              }
+              const unsigned mk = __ballot_sync(0xffffffffu, ok);
+              if (ok) {
+                s.stamp[i] = epoch;
+                s.ds[i] = bv;
+                s.par_s[i] = ks;
+                s.vislist[nvis + __popc(mk & ((1u << lane) - 1u))] = i;
+              }
+              nvis += __popc(mk);
+              __syncwarp();
+            }
           }
-          const unsigned mk = __ballot_sync(0xffffffffu, ok);
-          if (ok) {
-            const int slot = nvis + __popc(mk & ((1u << lane) - 1u));
-            s.act[i] = epoch;
-            s.ds[i] = bv;
-            s.par_s[i] = bk;
-            s.vislist[slot] = i;
-          }
-          nvis += __popc(mk);
         }
-        __syncwarp();
         // relax my unsettled sinks through the newly reached sources
-        for (int q = first_new; q < nvis; ++q) {
-          const int i = s.vislist[q];
-          const double ui = s.u[i];
-          if (!set0) {
-            const double nd = bv + fmax(ot_cost(s, i, k0) - ui - s.v[k0], 0.0);
-            if (nd < d0 || (nd == d0 && i < p0_)) { d0 = nd; p0_ = i; }
-          }
-          if (!set1) {
-            const double nd = bv + fmax(ot_cost(s, i, k1) - ui - s.v[k1], 0.0);
-            if (nd < d1 || (nd == d1 && i < p1_)) { d1 = nd; p1_ = i; }
+        if (!set0 || !set1) {
+          for (int q = first_new; q < nvis; ++q) {
+            const int i = s.vislist[q];
+            const double ui = s.u[i];
+            if (!set0) {
+              const double nd = bv + fmax(s.Cm[i * M + k0] - ui - v0, 0.0) + 0.0;
+              if (nd < d0 || (nd == d0 && i < p0_)) { d0 = nd; p0_ = i; }
+            }
+            if (!set1) {
+              const double nd = bv + fmax(s.Cm[i * M + k1] - ui - v1, 0.0) + 0.0;
+              if (nd < d1 || (nd == d1 && i < p1_)) { d1 = nd; p1_ = i; }
+            }
           }
         }
       }
       if (target < 0) { fail |= 2; break; }
-      // publish the parents of the settled sinks and of the target; potentials (common shifts dropped, see header):
-      // visited sources u += D - ds; sources with excess: lazy +D; settled sinks v -= D - dk
       if (set0 || k0 == target) s.par_k[k0] = p0_;
       if (has1 && (set1 || k1 == target)) s.par_k[k1] = p1_;
-      if (set0) s.v[k0] -= D - d0;
-      if (has1 && set1) s.v[k1] -= D - d1;
+      if (set0) s.v[k0] = v0 - (D - d0);
+      if (has1 && set1) s.v[k1] = v1 - (D - d1);
       for (int q = lane; q < nvis; q += 32) {
         const int i = s.vislist[q];
         s.u[i] += D - s.ds[i];
@@ -324,23 +340,22 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
       if (lane == 0) {
         int delta = s.deficit[target];
         int k = target, i = s.par_k[k], hops = 0;
-        while (true) {
-          const bool mid = s.excess[i] == 0;           // reached through a backward arc
-          if (!mid) { delta = min(delta, s.excess[i]); break; }
+        while (s.excess[i] == 0) {                     // reached through a backward arc
           const int pk = s.par_s[i];
           delta = min(delta, X(i, pk));
           k = pk;
           i = s.par_k[k];
           if (++hops > 2 * M + 2) { fail |= 4; delta = 0; break; }
         }
+        delta = min(delta, s.excess[i]);
         if (delta > 0) {
           k = target;
           i = s.par_k[k];
           s.deficit[target] -= delta;
           while (true) {
             const int xf = X(i, k);
-            if (xf == 0) setFL(k, s.fl_cnt[k]++, i);   // i starts feeding k
-            setX(i, k, xf + delta);
+            if (xf == 0) s.fls[k * n + s.fl_cnt[k]++] = (short)i;      // i starts feeding k
+            s.xs[i * M + k] = (signed char)(xf + delta);
             if (s.excess[i] > 0) {
               s.excess[i] -= delta;
               if (s.excess[i] == 0) left = i;
@@ -348,12 +363,12 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
             }
             const int pk = s.par_s[i];
             const int xb = X(i, pk) - delta;
-            setX(i, pk, xb);
+            s.xs[i * M + pk] = (signed char)xb;
             if (xb == 0) {                             // i stops feeding pk: swap-remove it from pk's list
               const int c = --s.fl_cnt[pk];
               int q = 0;
-              while (q < c && FL(pk, q) != i) ++q;
-              setFL(pk, q, FL(pk, c));
+              while (q < c && (int)s.fls[pk * n + q] != i) ++q;
+              s.fls[pk * n + q] = s.fls[pk * n + c];
             }
             k = pk;
             i = s.par_k[k];
@@ -382,16 +397,16 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const int k = t == 0 ? k0 : k1;
-          if (k < M && s.red_i[k] == left) {
+          if (k < M && s.base_i[k] == left) {
             double best = INFINITY;
             int bi = 0x7fffffff;
             for (int q = 0; q < nex; ++q) {
               const int i = s.exl[q];
-              const double c = ot_cost(s, i, k) - s.u[i];
+              const double c = s.Cm[i * M + k] - s.u[i];
               if (c < best || (c == best && i < bi)) { best = c; bi = i; }
             }
-            s.red_v[k] = best;
-            s.red_i[k] = bi;
+            s.base_v[k] = best;
+            s.base_i[k] = bi;
           }
         }
       }
@@ -402,25 +417,25 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
   }
   __syncthreads();
   // ---- value and keypoint gradients from the (constant) plan T = x / (n * M) ----
+  int* xg = flow + (long)p0 * M;
   const double unit = 1.0 / ((double)n * (double)M);
   double tot = 0.0;
   for (int o = tid; o < n * M; o += LOSS_THREADS) {
-    const int i = o / M, k = o - i * M;
-    const int f = X(i, k);
-    if (FLOW_SMEM) xg[o] = f;                        // publish the plan
-    if (f) tot += (double)f * ot_cost(s, i, k);
+    const int f = (int)s.xs[o];
+    xg[o] = f;                                       // publish the plan
+    if (f) tot += (double)f * s.Cm[o];
   }
-  tot = block_sum_d(tot, s.red_v) * unit;
+  tot = block_sum_d(tot, red) * unit;
   if (tid == 0) {
     parts[(long)b * 4 + 1] = tot;
-    parts[(long)b * 4 + 3] = (double)n_aug + 1e-9 * (double)n_pop;     // solver statistics: augmentations + 1e-9 * sinks settled
+    parts[(long)b * 4 + 3] = (double)n_aug + 1e-9 * (double)n_pop;     // solver statistics: augmentations + 1e-9 * search rounds
   }
   const double gsc = 2.0 * unit * w_ot / (double)B;
   for (int o = tid; o < M * 6; o += LOSS_THREADS) {
     const int k = o / 6, q = o - k * 6;
     double t = 0.0;
     for (int i = 0; i < n; ++i) {
-      const int f = X(i, k);
+      const int f = (int)s.xs[i * M + k];
       if (f) t += (double)f * (s.Y[k * 6 + q] - s.P[i * 6 + q]);
     }
     const int side = q / 3, c = q - side * 3;
@@ -445,7 +460,7 @@ __global__ void loss_total_kernel(int n_pairs, const double* __restrict__ parts,
 extern "C" size_t eqd_losses_workspace_bytes(int32_t n_rec_nodes, int32_t n_pocket_total) {
   const size_t a = ((size_t)(n_rec_nodes > 0 ? n_rec_nodes : 1) * 8 + 255) & ~(size_t)255;
   const size_t f = ((size_t)(n_pocket_total > 0 ? n_pocket_total : 1) * EQD_HEADS * 4 + 255) & ~(size_t)255;
-  return a + 2 * f + 256;      // flows, per-sink source lists
+  return a + f + f / 2 + 256 + 2 * f + 256;      // flows (int32), per-sink source lists (int16), cost matrix (fp64)
 }
 
 // parts[B][4] = {mse, ot, intersection, -} per pair; total[4] = {loss, mean mse, mean ot, mean intersection};
@@ -468,8 +483,8 @@ extern "C" int eqd_losses(const eqd_graph* g, const float* pred_lig, const float
   double* wrec = reinterpret_cast<double*>(w);
   const size_t fbytes = ((size_t)(n_pocket_total > 0 ? n_pocket_total : 1) * EQD_HEADS * 4 + 255) & ~(size_t)255;
   int* flow = reinterpret_cast<int*>(w + (((size_t)(n_rec > 0 ? n_rec : 1) * 8 + 255) & ~(size_t)255));
-  int* lists = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(flow) + fbytes);
-
+  short* lists = reinterpret_cast<short*>(reinterpret_cast<unsigned char*>(flow) + fbytes);
+  double* cost = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(lists) + fbytes / 2 + 256 - ((fbytes / 2) & 255));
   cudaError_t me = cudaMemsetAsync(err_flags, 0, sizeof(int32_t), st);
   if (me != cudaSuccess) return -(1000 + (int)me);
   eqd::loss_mse_intersection_kernel<<<g->n_pairs, LOSS_THREADS, 0, st>>>(*g, pred_lig, bound_lig, bound_rec, (double)sigma,
@@ -478,17 +493,10 @@ extern "C" int eqd_losses(const eqd_graph* g, const float* pred_lig, const float
   EQD_CUDA_LAUNCH_CHECK();
   int cap = max_pocket > 0 ? max_pocket : 1;
   if (cap > OT_MAX_POCKET) cap = OT_MAX_POCKET;            // larger pockets are flagged by the kernel (err bit 1)
-  if (cap <= OT_SMEM_CAP) {
-    const size_t smem = eqd::ot_smem_bytes(cap, true);
-    EQD_SET_SMEM((eqd::ot_emd_kernel<true>), smem);
-    eqd::ot_emd_kernel<true><<<g->n_pairs, LOSS_THREADS, smem, st>>>(g->n_pairs, cap, pocket_ptr, pocket_lig, pocket_rec, keypts,
-                                                                    (double)w_ot, flow, lists, parts, dkeypts, err_flags);
-  } else {
-    const size_t smem = eqd::ot_smem_bytes(cap, false);
-    EQD_SET_SMEM((eqd::ot_emd_kernel<false>), smem);
-    eqd::ot_emd_kernel<false><<<g->n_pairs, LOSS_THREADS, smem, st>>>(g->n_pairs, cap, pocket_ptr, pocket_lig, pocket_rec, keypts,
-                                                                     (double)w_ot, flow, lists, parts, dkeypts, err_flags);
-  }
+  const size_t smem = eqd::ot_layout(cap).bytes;
+  EQD_SET_SMEM((eqd::ot_emd_kernel), smem);
+  eqd::ot_emd_kernel<<<g->n_pairs, LOSS_THREADS, smem, st>>>(g->n_pairs, cap, pocket_ptr, pocket_lig, pocket_rec, keypts,
+                                                            (double)w_ot, flow, lists, cost, parts, dkeypts, err_flags);
   EQD_CUDA_LAUNCH_CHECK();
   eqd::loss_total_kernel<<<1, 32, 0, st>>>(g->n_pairs, parts, (double)w_ot, (double)w_int, total);
   EQD_CUDA_LAUNCH_CHECK();
