@@ -308,18 +308,27 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
             }
           }
         }
-        // relax my unsettled sinks through the newly reached sources
+        // relax my unsettled sinks through the newly reached sources; 8 sources per step so that the dependent
+        // shared-memory loads (list -> potential, cost row) of different sources overlap
         if (!set0 || !set1) {
-          for (int q = first_new; q < nvis; ++q) {
-            const int i = s.vislist[q];
-            const double ui = s.u[i];
-            if (!set0) {
-              const double nd = bv + fmax(s.Cm[i * M + k0] - ui - v0, 0.0) + 0.0;
-              if (nd < d0 || (nd == d0 && i < p0_)) { d0 = nd; p0_ = i; }
+          for (int q = first_new; q < nvis; q += 8) {
+            int ii[8];
+            double c0[8], c1[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) ii[t] = s.vislist[min(q + t, nvis - 1)];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const double ui = s.u[ii[t]];
+              c0[t] = s.Cm[ii[t] * M + k0] - ui;
+              c1[t] = has1 ? s.Cm[ii[t] * M + k1] - ui : 0.0;
             }
-            if (!set1) {
-              const double nd = bv + fmax(s.Cm[i * M + k1] - ui - v1, 0.0) + 0.0;
-              if (nd < d1 || (nd == d1 && i < p1_)) { d1 = nd; p1_ = i; }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              if (q + t < nvis) {
+                const double nd0 = fmax(c0[t] - v0, 0.0) + bv, nd1 = fmax(c1[t] - v1, 0.0) + bv;
+                if (!set0 && (nd0 < d0 || (nd0 == d0 && ii[t] < p0_))) { d0 = nd0; p0_ = ii[t]; }
+                if (!set1 && (nd1 < d1 || (nd1 == d1 && ii[t] < p1_))) { d1 = nd1; p1_ = ii[t]; }
+              }
             }
           }
         }
@@ -400,10 +409,16 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
           if (k < M && s.base_i[k] == left) {
             double best = INFINITY;
             int bi = 0x7fffffff;
-            for (int q = 0; q < nex; ++q) {
-              const int i = s.exl[q];
-              const double c = s.Cm[i * M + k] - s.u[i];
-              if (c < best || (c == best && i < bi)) { best = c; bi = i; }
+            for (int q = 0; q < nex; q += 4) {
+              int ii[4];
+              double cc[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) ii[t] = s.exl[min(q + t, nex - 1)];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) cc[t] = s.Cm[ii[t] * M + k] - s.u[ii[t]];
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                if (q + t < nex && (cc[t] < best || (cc[t] == best && ii[t] < bi))) { best = cc[t]; bi = ii[t]; }
             }
             s.base_v[k] = best;
             s.base_i[k] = bi;
