@@ -43,6 +43,7 @@ def main():
     out = tr.step(g, t)
     torch.cuda.synchronize()
     w_dp = tr.flat_w.clone()
+    g_dp = tr.flat_g.clone()          # the all-reduced, averaged (and clipped) gradient the optimiser consumed
     gathered = [torch.zeros_like(w_dp) for _ in range(world)]
     dist.all_gather(gathered, w_dp)
     if rank == 0:
@@ -52,10 +53,14 @@ def main():
         g, t = batch(range(per * world))
         ref.step(g, t)
         torch.cuda.synchronize()
-        diff = (ref.flat_w - w_dp).abs().max().item()
-        upd = (ref.flat_w - torch.cat([p.detach().reshape(-1) for p in []] or [ref.flat_w * 0])).abs().max().item()
-        print(f'ddp_check: world {world}: max |w_dp - w_global_batch| = {diff:.3e} (lr 1e-3 => update size 1e-3)', flush=True)
-        assert diff < 2e-6, diff
+        gmax = ref.flat_g.abs().max().item()
+        gdiff = (ref.flat_g - g_dp).abs().max().item()
+        wdiff = (ref.flat_w - w_dp).abs().max().item()
+        print(f'ddp_check: world {world}: max |g_dp - g_global_batch| = {gdiff:.3e} (max |g| = {gmax:.3e}); '
+              f'max |w_dp - w_global_batch| = {wdiff:.3e} (Adam step 1 moves every weight by ~lr = 1e-3 whatever its '
+              f'gradient, so near-zero gradients amplify rounding)', flush=True)
+        assert gdiff <= 2e-5 * gmax, (gdiff, gmax)
+        assert wdiff < 5e-4, wdiff
         print('ddp_check: OK', flush=True)
     dist.barrier()
     dist.destroy_process_group()
