@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libeqd_iegmn.so')
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 EDGE_FEATS, N_RBF, HID, H0, H0_PAD, N_RES_TYPES, HEADS, TILE_ROWS = 27, 15, 64, 69, 72, 21, 50, 128
 STATUS_SVD_DEGENERATE, STATUS_NAN, STATUS_DEGREE_OVERFLOW, STATUS_BAD_RESIDUE = 1, 2, 4, 8
 
@@ -30,11 +30,20 @@ class EqdLayerParams(C.Structure):
     _fields_ = [('dh', _i32), ('dhp', _i32),
                 ('w_proj', _vp), ('b_proj', _vp), ('w_edge1', _vp), ('edge_ln_g', _vp), ('edge_ln_b', _vp),
                 ('w_edge2', _vp), ('b_edge2', _vp), ('w_coor1', _vp), ('b_coor1', _vp), ('w_coor2', _vp),
-                ('b_coor2', _f32), ('w_edge_tc', _vp), ('edge_consts_host', _vp),
-                ('w_node_tc', _vp), ('node_consts_host', _vp), ('w_proj_tc', _vp), ('proj_bias_host', _vp),
+                ('b_coor2', _f32), ('w_edge_tc', _vp), ('w_node_tc', _vp), ('w_proj_tc', _vp),
                 ('w_node1', _vp), ('b_node1', _vp), ('node_ln_g', _vp), ('node_ln_b', _vp),
                 ('w_node2', _vp), ('b_node2', _vp),
                 ('skip_weight_h', _f32), ('x_connection_init', _f32), ('leaky_slope', _f32)]
+
+
+class EqdLayerConsts(C.Structure):
+    """eqd_layer_consts: launch-time constants of the tensor-core kernels, host VALUES (not pointers)."""
+    _fields_ = [('edge', _f32 * 64 * 5), ('node', _f32 * 304), ('proj_bias', _f32 * 320)]
+
+
+class EqdLayer(C.Structure):
+    """eqd_layer: what the entry points take -- `dev` (device pointers + scalars, passed to kernels by value) + `consts`."""
+    _fields_ = [('dev', EqdLayerParams), ('consts', EqdLayerConsts)]
 
 
 class EqdForwardIO(C.Structure):
@@ -48,7 +57,7 @@ class EqdHeadParams(C.Structure):
 
 
 # symbol -> (restype, argtypes); every symbol include/eqd_iegmn.h declares must be listed here
-_G, _L, _H = C.POINTER(EqdGraph), C.POINTER(EqdLayerParams), C.POINTER(EqdHeadParams)
+_G, _L, _H = C.POINTER(EqdGraph), C.POINTER(EqdLayer), C.POINTER(EqdHeadParams)
 PROTOTYPES = {
     'eqd_abi_version': (C.c_int, []),
     'eqd_workspace_bytes': (C.c_size_t, [_i32, _i32, _i32]),

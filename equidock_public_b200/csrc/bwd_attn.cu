@@ -256,8 +256,9 @@ bwd_attn_dkv_kernel(eqd_graph g, float slope, const float* __restrict__ proj, co
 
 }  // namespace eqd
 
-extern "C" int eqd_bwd_attention(const eqd_graph* g, const eqd_layer_params* p, const float* proj, const float* mu,
+extern "C" int eqd_bwd_attention(const eqd_graph* g, const eqd_layer* p_l, const float* proj, const float* mu,
                                  int32_t ldmu, const float* dmu, float* dP, float* rowstat, void* stream) {
+  const eqd_layer_params* p = p_l ? &p_l->dev : nullptr;
   if (!g || !p || !proj || !mu || !dmu || !dP || !rowstat) return EQD_ERR_BAD_ARG;
   const bool extra = (p->dh == 69 && p->dhp == 72);
   if (!extra && !(p->dh == 64 && p->dhp == 64)) return EQD_ERR_UNSUPPORTED;

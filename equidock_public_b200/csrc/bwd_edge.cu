@@ -340,10 +340,11 @@ __global__ void bwd_edge_gather_kernel(eqd_graph g, const int* __restrict__ out_
 
 }  // namespace eqd
 
-extern "C" int eqd_bwd_edge(const eqd_graph* g, const eqd_layer_params* p, const float* w2lin, const float* w3lin,
+extern "C" int eqd_bwd_edge(const eqd_graph* g, const eqd_layer* p_l, const float* w2lin, const float* w3lin,
                             const float* proj, const double* x_in, const float* daggr, const double* dx_out,
                             float* ein_out, float* n1_out, float* msg_out, float* dz3_out, float* dmsg_out, float* dz1_out,
                             double* dxrel_out, float* vec_partial, int32_t* n_partials_out, void* stream) {
+  const eqd_layer_params* p = p_l ? &p_l->dev : nullptr;
   if (!g || !p || !w2lin || !w3lin || !proj || !x_in || !daggr || !dx_out || !ein_out || !n1_out || !msg_out || !dz3_out ||
       !dmsg_out || !dz1_out || !dxrel_out || !vec_partial)
     return EQD_ERR_BAD_ARG;

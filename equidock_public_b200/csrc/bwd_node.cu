@@ -275,11 +275,12 @@ bwd_node_mlp_kernel(int n_nodes, eqd_layer_params p, const float* __restrict__ w
 
 }  // namespace eqd
 
-extern "C" int eqd_bwd_node_mlp(const eqd_graph* g, const eqd_layer_params* p, const float* w_node1_lin,
+extern "C" int eqd_bwd_node_mlp(const eqd_graph* g, const eqd_layer* p_l, const float* w_node1_lin,
                                 const float* w_node2_lin, const float* h_in, int32_t ldh, const float* aggr,
                                 const float* mu, int32_t ldmu, const float* h0, const float* dh_out, float* dh_in,
                                 float* daggr, float* dmu, float* dh0_acc, float* n5_out, float* du_out,
                                 float* vec_partial, int32_t* n_partials_out, void* stream) {
+  const eqd_layer_params* p = p_l ? &p_l->dev : nullptr;
   if (!g || !p || !w_node1_lin || !w_node2_lin || !h_in || !aggr || !mu || !h0 || !dh_out || !dh_in || !daggr || !dmu ||
       !dh0_acc || !n5_out || !du_out || !vec_partial)
     return EQD_ERR_BAD_ARG;

@@ -72,8 +72,9 @@ __global__ void bwd_embed_kernel(eqd_graph g, const float* __restrict__ res_l, c
 
 }  // namespace eqd
 
-extern "C" int eqd_bwd_project(const eqd_graph* g, const eqd_layer_params* p, const float* w_projT, const float* dP,
+extern "C" int eqd_bwd_project(const eqd_graph* g, const eqd_layer* p_l, const float* w_projT, const float* dP,
                                float* dh, void* stream) {
+  const eqd_layer_params* p = p_l ? &p_l->dev : nullptr;
   if (!g || !p || !w_projT || !dP || !dh) return EQD_ERR_BAD_ARG;
   const bool extra = (p->dh == 69 && p->dhp == 72);
   if (!extra && !(p->dh == 64 && p->dhp == 64)) return EQD_ERR_UNSUPPORTED;

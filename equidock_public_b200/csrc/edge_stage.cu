@@ -183,8 +183,9 @@ edge_stage_kernel(eqd_graph g, eqd_layer_params p, const float* __restrict__ pro
 
 }  // namespace eqd
 
-extern "C" int eqd_edge_stage_ffma(const eqd_graph* g, const eqd_layer_params* p, const float* proj, const double* x_in,
+extern "C" int eqd_edge_stage_ffma(const eqd_graph* g, const eqd_layer* p_l, const float* proj, const double* x_in,
                               const double* x_orig, float* aggr, double* x_out, int32_t* status, void* stream) {
+  const eqd_layer_params* p = p_l ? &p_l->dev : nullptr;
   if (!g || !p || !proj || !x_in || !x_orig || !aggr || !x_out || !status) return EQD_ERR_BAD_ARG;
   if (g->max_in_degree < 1 || g->max_in_degree > EQD_TM) return EQD_ERR_UNSUPPORTED;
   if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)

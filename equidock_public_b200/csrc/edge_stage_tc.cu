@@ -423,10 +423,11 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
 
 EQD_TRACE_SETTER(eqd_trace_set_edge)
 
-extern "C" int eqd_edge_stage(const eqd_graph* g, const eqd_layer_params* p, const float* proj, const double* x_in,
+extern "C" int eqd_edge_stage(const eqd_graph* g, const eqd_layer* p_l, const float* proj, const double* x_in,
                               const double* x_orig, float* aggr, double* x_out, int32_t* status, void* stream) {
+  const eqd_layer_params* p = p_l ? &p_l->dev : nullptr;
   if (!g || !p || !proj || !x_in || !x_orig || !aggr || !x_out || !status) return EQD_ERR_BAD_ARG;
-  if (!p->w_edge_tc || !p->edge_consts_host) return EQD_ERR_BAD_ARG;
+  if (!p->w_edge_tc) return EQD_ERR_BAD_ARG;
   if (g->max_in_degree < 1 || g->max_in_degree > EQD_TM) return EQD_ERR_UNSUPPORTED;
   if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)
   if ((reinterpret_cast<uintptr_t>(g->he_lig) | reinterpret_cast<uintptr_t>(g->he_rec) |
@@ -437,7 +438,7 @@ extern "C" int eqd_edge_stage(const eqd_graph* g, const eqd_layer_params* p, con
   if (tn > TC_MAX_TN) tn = TC_MAX_TN;
   int ntiles = (g->n_nodes + tn - 1) / tn;
   eqd::EdgeConsts cst;
-  memcpy(&cst, p->edge_consts_host, sizeof(cst));
+  memcpy(&cst, p_l->consts.edge, sizeof(cst));
   size_t smem = sizeof(eqd::TcSmem) + 128;
   EQD_SET_SMEM((eqd::edge_stage_tc_kernel), smem);
   int grid = (ntiles + 1) / 2;

@@ -89,8 +89,9 @@ extern "C" int eqd_embed(const eqd_graph* g, const float* emb, const float* res_
   return eqd_embed_checked(g, emb, res_feat_lig, res_feat_rec, mu_lig, mu_rec, x_lig, x_rec, h0, x64, nullptr, stream);
 }
 
-extern "C" int eqd_project(const eqd_graph* g, const eqd_layer_params* p, const float* h, int32_t ldh, float* proj,
+extern "C" int eqd_project(const eqd_graph* g, const eqd_layer* p_l, const float* h, int32_t ldh, float* proj,
                            void* stream) {
+  const eqd_layer_params* p = p_l ? &p_l->dev : nullptr;
   if (!g || !p || !h || !proj) return EQD_ERR_BAD_ARG;
   if (!((p->dh == 64 && p->dhp == 64) || (p->dh == 69 && p->dhp == 72))) return EQD_ERR_UNSUPPORTED;
   if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)

@@ -81,7 +81,7 @@ extern "C" int eqd_forward_stash_offsets(const eqd_graph* g, int32_t n_layers, s
   return EQD_OK;
 }
 
-extern "C" int eqd_iegmn_forward(const eqd_graph* g, const eqd_layer_params* const* layers, int32_t n_layers,
+extern "C" int eqd_iegmn_forward(const eqd_graph* g, const eqd_layer* const* layers, int32_t n_layers,
                                  const eqd_head_params* hp, const eqd_forward_io* io, void* workspace,
                                  size_t workspace_bytes, void* stream) {
   if (!g || !layers || n_layers < 1 || !hp || !io || !workspace) return EQD_ERR_BAD_ARG;
@@ -141,17 +141,20 @@ extern "C" int eqd_iegmn_forward(const eqd_graph* g, const eqd_layer_params* con
   int rc = eqd_embed_checked(g, io->emb, io->res_lig, io->res_rec, io->mu_lig, io->mu_rec, io->x_lig, io->x_rec, h0, x0,
                              io->status, stream);
   if (rc) return rc;
-  const eqd_layer_params* l0 = layers[0];
+  const eqd_layer* l0_l = layers[0];
+  const eqd_layer_params* l0 = &l0_l->dev;
   const bool tc0 = l0->dh == EQD_H0 && l0->w_proj_tc && l0->w_node_tc && !io->layer0_fp32;
-  if (tc0) rc = eqd_project_tc0(g, l0, h0, pa, kv, x5, stream);
-  else rc = eqd_project(g, l0, h0, l0->dh == EQD_H0 ? EQD_H0_PAD : EQD_HID, pa, stream);
+  if (tc0) rc = eqd_project_tc0(g, l0_l, h0, pa, kv, x5, stream);
+  else rc = eqd_project(g, l0_l, h0, l0->dh == EQD_H0 ? EQD_H0_PAD : EQD_HID, pa, stream);
   if (rc) return rc;
   const float* h_in = h0;
   int ldh = l0->dh == EQD_H0 ? EQD_H0_PAD : EQD_HID;
   const double* x_in = x0;
   for (int li = 0; li < n_layers; ++li) {
-    const eqd_layer_params* lp = layers[li];
-    const eqd_layer_params* lpn = li + 1 < n_layers ? layers[li + 1] : nullptr;
+    const eqd_layer* lp_l = layers[li];
+    const eqd_layer* lpn_l = li + 1 < n_layers ? layers[li + 1] : nullptr;
+    const eqd_layer_params* lp = &lp_l->dev;
+    const eqd_layer_params* lpn = lpn_l ? &lpn_l->dev : nullptr;
     const bool last = lpn == nullptr;
     float* h_out = last ? io->h_out : hbuf[li & 1];
     double* x_out = last ? io->x_out : xbuf[li & 1];
@@ -164,16 +167,16 @@ extern "C" int eqd_iegmn_forward(const eqd_graph* g, const eqd_layer_params* con
       mu = reinterpret_cast<float*>(sb + sl.mu + (size_t)li * sl.m_stride);
     }
     stage_event(li, 0);
-    rc = eqd_edge_stage(g, lp, pa, x_in, x0, aggr, x_out, io->status, stream);
+    rc = eqd_edge_stage(g, lp_l, pa, x_in, x0, aggr, x_out, io->status, stream);
     if (rc) return rc;
     stage_event(li, 1);
     stage_event(li, 2);
     if (lp->dh == EQD_HID && lp->w_node_tc && (!lpn || lpn->w_proj_tc)) {
-      rc = eqd_node_stage_tc(g, lp, lpn, h_in, h0, pa, aggr, kv, mu, h_out, pb, stream);
+      rc = eqd_node_stage_tc(g, lp_l, lpn_l, h_in, h0, pa, aggr, kv, mu, h_out, pb, stream);
     } else if (li == 0 && tc0 && (!lpn || lpn->w_proj_tc)) {
-      rc = eqd_node_stage_tc0(g, lp, lpn, h0, pa, aggr, kv, x5, mu, h_out, pb, stream);
+      rc = eqd_node_stage_tc0(g, lp_l, lpn_l, h0, pa, aggr, kv, x5, mu, h_out, pb, stream);
     } else {   // fp32 CUDA-core node stage (fused projections); the next layer's tensor-core attention needs K/V blocks
-      rc = eqd_node_stage(g, lp, lpn, h_in, ldh, h0, pa, aggr, h_out, pb, stream);
+      rc = eqd_node_stage(g, lp_l, lpn_l, h_in, ldh, h0, pa, aggr, h_out, pb, stream);
       if (!rc && lpn && lpn->dh == EQD_HID && lpn->w_node_tc) rc = eqd_kv_blocks(g, pb, 320, 192, 256, kv, stream);
     }
     if (rc) return rc;

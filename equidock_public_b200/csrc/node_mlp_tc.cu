@@ -482,15 +482,16 @@ node_mlp0_tc_kernel(int n_nodes, eqd_layer_params p, const __grid_constant__ Nm0
 
 EQD_TRACE_SETTER(eqd_trace_set_mlp)
 
-extern "C" int eqd_node_mlp_tc(const eqd_graph* g, const eqd_layer_params* p, const float* h_in, const float* aggr,
+extern "C" int eqd_node_mlp_tc(const eqd_graph* g, const eqd_layer* p_l, const float* h_in, const float* aggr,
                                const float* mu, const float* h0, float* h_out, void* stream) {
+  const eqd_layer_params* p = p_l ? &p_l->dev : nullptr;
   if (!g || !p || !h_in || !aggr || !mu || !h0 || !h_out) return EQD_ERR_BAD_ARG;
   if (p->dh != 64 || p->dhp != 64) return EQD_ERR_UNSUPPORTED;
   if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)
-  if (!p->w_node_tc || !p->node_consts_host || (reinterpret_cast<uintptr_t>(p->w_node_tc) & 15)) return EQD_ERR_BAD_ARG;
+  if (!p->w_node_tc || (reinterpret_cast<uintptr_t>(p->w_node_tc) & 15)) return EQD_ERR_BAD_ARG;
   if (g->n_nodes <= 0) return EQD_OK;
   eqd::NmConsts cst;
-  memcpy(&cst, p->node_consts_host, sizeof(cst));
+  memcpy(&cst, p_l->consts.node, sizeof(cst));
   int ntiles = (g->n_nodes + EQD_TM - 1) / EQD_TM;
   size_t smem = sizeof(eqd::NmSmem) + 128;
   EQD_SET_SMEM((eqd::node_mlp_tc_kernel), smem);
@@ -501,15 +502,16 @@ extern "C" int eqd_node_mlp_tc(const eqd_graph* g, const eqd_layer_params* p, co
   return EQD_OK;
 }
 
-extern "C" int eqd_node_mlp_tc0(const eqd_graph* g, const eqd_layer_params* p, const float* h0, const float* aggr,
+extern "C" int eqd_node_mlp_tc0(const eqd_graph* g, const eqd_layer* p_l, const float* h0, const float* aggr,
                                 const float* mu, float* h_out, void* stream) {
+  const eqd_layer_params* p = p_l ? &p_l->dev : nullptr;
   if (!g || !p || !h0 || !aggr || !mu || !h_out) return EQD_ERR_BAD_ARG;
   if (p->dh != 69 || p->dhp != 72) return EQD_ERR_UNSUPPORTED;
   if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)
-  if (!p->w_node_tc || !p->node_consts_host || (reinterpret_cast<uintptr_t>(p->w_node_tc) & 15)) return EQD_ERR_BAD_ARG;
+  if (!p->w_node_tc || (reinterpret_cast<uintptr_t>(p->w_node_tc) & 15)) return EQD_ERR_BAD_ARG;
   if (g->n_nodes <= 0) return EQD_OK;
   eqd::Nm0Consts cst;
-  memcpy(&cst, p->node_consts_host, sizeof(cst));
+  memcpy(&cst, p_l->consts.node, sizeof(cst));
   int ntiles = (g->n_nodes + EQD_TM - 1) / EQD_TM;
   size_t smem = sizeof(eqd::Nm0Smem) + 128;
   EQD_SET_SMEM((eqd::node_mlp0_tc_kernel), smem);
@@ -523,31 +525,35 @@ extern "C" int eqd_node_mlp_tc0(const eqd_graph* g, const eqd_layer_params* p, c
 extern "C" int eqd_attention_tc0(const eqd_graph*, const float*, const void*, const float*, float*, void*);
 
 // Layer 0 (dh == 69): attention (64 tensor-core channels + 5 fp32 ones), node MLP, next layer's projections.
-extern "C" int eqd_node_stage_tc0(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next,
+extern "C" int eqd_node_stage_tc0(const eqd_graph* g, const eqd_layer* p_l, const eqd_layer* p_next_l,
                                   const float* h0, const float* proj, const float* aggr, void* kv, const float* x5,
                                   float* mu, float* h_out, float* proj_next, void* stream) {
+  const eqd_layer_params* p = p_l ? &p_l->dev : nullptr;
+  const eqd_layer_params* p_next = p_next_l ? &p_next_l->dev : nullptr;
   if (!g || !p || !kv || !mu || !x5) return EQD_ERR_BAD_ARG;
   if (p_next && !proj_next) return EQD_ERR_BAD_ARG;
   int rc = eqd_attention_tc0(g, proj, kv, x5, mu, stream);
   if (rc) return rc;
-  rc = eqd_node_mlp_tc0(g, p, h0, aggr, mu, h_out, stream);
+  rc = eqd_node_mlp_tc0(g, p_l, h0, aggr, mu, h_out, stream);
   if (rc) return rc;
-  if (p_next) rc = eqd_project_tc(g, p_next, h_out, proj_next, kv, stream);
+  if (p_next) rc = eqd_project_tc(g, p_next_l, h_out, proj_next, kv, stream);
   return rc;
 }
 
-extern "C" int eqd_project_tc(const eqd_graph*, const eqd_layer_params*, const float*, float*, void*, void*);
+extern "C" int eqd_project_tc(const eqd_graph*, const eqd_layer*, const float*, float*, void*, void*);
 extern "C" int eqd_attention_tc(const eqd_graph*, const float*, const void*, float*, void*);
 
-extern "C" int eqd_node_stage_tc(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next,
+extern "C" int eqd_node_stage_tc(const eqd_graph* g, const eqd_layer* p_l, const eqd_layer* p_next_l,
                                  const float* h_in, const float* h0, const float* proj, const float* aggr, void* kv,
                                  float* mu, float* h_out, float* proj_next, void* stream) {
+  const eqd_layer_params* p = p_l ? &p_l->dev : nullptr;
+  const eqd_layer_params* p_next = p_next_l ? &p_next_l->dev : nullptr;
   if (!g || !p || !kv || !mu) return EQD_ERR_BAD_ARG;
   if (p_next && !proj_next) return EQD_ERR_BAD_ARG;
   int rc = eqd_attention_tc(g, proj, kv, mu, stream);
   if (rc) return rc;
-  rc = eqd_node_mlp_tc(g, p, h_in, aggr, mu, h0, h_out, stream);
+  rc = eqd_node_mlp_tc(g, p_l, h_in, aggr, mu, h0, h_out, stream);
   if (rc) return rc;
-  if (p_next) rc = eqd_project_tc(g, p_next, h_out, proj_next, kv, stream);
+  if (p_next) rc = eqd_project_tc(g, p_next_l, h_out, proj_next, kv, stream);
   return rc;
 }

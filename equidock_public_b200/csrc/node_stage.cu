@@ -177,9 +177,11 @@ node_stage_kernel(eqd_graph g, eqd_layer_params p, eqd_layer_params pn, int has_
 
 }  // namespace eqd
 
-extern "C" int eqd_node_stage(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next,
+extern "C" int eqd_node_stage(const eqd_graph* g, const eqd_layer* p_l, const eqd_layer* p_next_l,
                               const float* h_in, int32_t ldh, const float* h0, const float* proj, const float* aggr,
                               float* h_out, float* proj_next, void* stream) {
+  const eqd_layer_params* p = p_l ? &p_l->dev : nullptr;
+  const eqd_layer_params* p_next = p_next_l ? &p_next_l->dev : nullptr;
   if (!g || !p || !h_in || !h0 || !proj || !aggr || !h_out) return EQD_ERR_BAD_ARG;
   if (p_next && (!proj_next || p_next->dh != 64 || p_next->dhp != 64)) return EQD_ERR_BAD_ARG;
   const bool extra = (p->dh == 69 && p->dhp == 72);
@@ -206,11 +208,11 @@ extern "C" int eqd_node_stage(const eqd_graph* g, const eqd_layer_params* p, con
   return EQD_OK;
 }
 
-extern "C" int eqd_iegmn_layer_forward(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next,
+extern "C" int eqd_iegmn_layer_forward(const eqd_graph* g, const eqd_layer* p_l, const eqd_layer* p_next_l,
                                        const float* h_in, int32_t ldh, const float* h0, const double* x_in,
                                        const double* x_orig, float* proj, float* proj_next, float* aggr, float* h_out,
                                        double* x_out, int32_t* status, void* stream) {
-  int rc = eqd_edge_stage(g, p, proj, x_in, x_orig, aggr, x_out, status, stream);
+  int rc = eqd_edge_stage(g, p_l, proj, x_in, x_orig, aggr, x_out, status, stream);
   if (rc) return rc;
-  return eqd_node_stage(g, p, p_next, h_in, ldh, h0, proj, aggr, h_out, proj_next, stream);
+  return eqd_node_stage(g, p_l, p_next_l, h_in, ldh, h0, proj, aggr, h_out, proj_next, stream);
 }

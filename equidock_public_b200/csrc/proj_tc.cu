@@ -254,14 +254,15 @@ extern "C" size_t eqd_kv_blocks_bytes(int32_t n_nodes) {
 }
 
 template <bool L0>
-static int launch_project_tc(const eqd_graph* g, const eqd_layer_params* p, const float* h, int ldh, float* proj, int pw,
+static int launch_project_tc(const eqd_graph* g, const eqd_layer* p_l, const float* h, int ldh, float* proj, int pw,
                              void* kv, float* x5, void* stream) {
+  const eqd_layer_params* p = &p_l->dev;
   if (!(p->leaky_slope >= 0.f && p->leaky_slope <= 1.f)) return EQD_ERR_UNSUPPORTED;  // lrelu() = max(v, slope*v)
-  if (!p->w_proj_tc || !p->proj_bias_host || (reinterpret_cast<uintptr_t>(p->w_proj_tc) & 15)) return EQD_ERR_BAD_ARG;
+  if (!p->w_proj_tc || (reinterpret_cast<uintptr_t>(p->w_proj_tc) & 15)) return EQD_ERR_BAD_ARG;
   if (g->n_nodes <= 0) return EQD_OK;
   eqd::PjConsts cst;
   memset(&cst, 0, sizeof(cst));
-  memcpy(&cst, p->proj_bias_host, 320 * sizeof(float));
+  memcpy(&cst, p_l->consts.proj_bias, 320 * sizeof(float));
   int ntiles = (g->n_nodes + EQD_TM - 1) / EQD_TM;
   size_t smem = sizeof(eqd::PjSmem<L0>) + 128;
   EQD_SET_SMEM((eqd::project_tc_kernel<L0>), smem);
@@ -274,18 +275,20 @@ static int launch_project_tc(const eqd_graph* g, const eqd_layer_params* p, cons
   return EQD_OK;
 }
 
-extern "C" int eqd_project_tc(const eqd_graph* g, const eqd_layer_params* p, const float* h, float* proj, void* kv,
+extern "C" int eqd_project_tc(const eqd_graph* g, const eqd_layer* p_l, const float* h, float* proj, void* kv,
                               void* stream) {
+  const eqd_layer_params* p = p_l ? &p_l->dev : nullptr;
   if (!g || !p || !h || !proj) return EQD_ERR_BAD_ARG;
   if (p->dh != 64 || p->dhp != 64) return EQD_ERR_UNSUPPORTED;
-  return launch_project_tc<false>(g, p, h, EQD_HID, proj, 320, kv, nullptr, stream);
+  return launch_project_tc<false>(g, p_l, h, EQD_HID, proj, 320, kv, nullptr, stream);
 }
 
-extern "C" int eqd_project_tc0(const eqd_graph* g, const eqd_layer_params* p, const float* h0, float* proj, void* kv,
+extern "C" int eqd_project_tc0(const eqd_graph* g, const eqd_layer* p_l, const float* h0, float* proj, void* kv,
                                float* x5, void* stream) {
+  const eqd_layer_params* p = p_l ? &p_l->dev : nullptr;
   if (!g || !p || !h0 || !proj || !kv || !x5) return EQD_ERR_BAD_ARG;
   if (p->dh != 69 || p->dhp != 72) return EQD_ERR_UNSUPPORTED;
-  return launch_project_tc<true>(g, p, h0, EQD_H0_PAD, proj, 128 + 3 * 72, kv, x5, stream);
+  return launch_project_tc<true>(g, p_l, h0, EQD_H0_PAD, proj, 128 + 3 * 72, kv, x5, stream);
 }
 
 extern "C" int eqd_kv_blocks(const eqd_graph* g, const float* proj, int32_t pw, int32_t koff, int32_t voff, void* kv,

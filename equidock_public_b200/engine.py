@@ -153,18 +153,19 @@ class PackedLayer:
             'node_ln_g': pad(f('node_mlp.3.weight')), 'node_ln_b': pad(f('node_mlp.3.bias')),
             'w_node2': w_node2, 'b_node2': b6, 'w_edge_tc': w_edge_tc,
         }, device)
-        s = nat.EqdLayerParams()
+        lay = nat.EqdLayer()
+        s = lay.dev
         s.dh, s.dhp = dh, dhp
         for k, v in self.t.items():
             if not k.startswith('_'):
                 setattr(s, k, v.data_ptr())
-        s.edge_consts_host = self.edge_consts_host.data_ptr()
-        if self.node_consts_host is not None:
-            s.node_consts_host = self.node_consts_host.data_ptr()
-            s.proj_bias_host = self.proj_bias_host.data_ptr()
+        for name, host in (('edge', self.edge_consts_host), ('node', self.node_consts_host), ('proj_bias', self.proj_bias_host)):
+            if host is not None:   # host VALUES, copied into the descriptor (the kernels get them as launch constants)
+                flat = host.reshape(-1).numpy()
+                C.memmove(C.addressof(getattr(lay.consts, name)), flat.ctypes.data, flat.nbytes)
         s.b_coor2 = float(sd['coors_mlp.4.bias'].detach().reshape(-1)[0].item())
         s.skip_weight_h, s.x_connection_init, s.leaky_slope = skip_weight_h, x_connection_init, leaky_slope
-        self.struct = s
+        self.struct = lay
 
 
 class PackedHead:
@@ -476,7 +477,7 @@ class IEGMNEngine:
             io.train_stash, io.train_stash_bytes = train_stash.data_ptr(), int(train_stash.numel())
         events = stage_timer.new_forward(len(layers)) if stage_timer is not None else None
         io.stage_events = C.cast(events, C.c_void_p) if events is not None else None
-        larr = (C.POINTER(nat.EqdLayerParams) * len(layers))(*[C.pointer(l.struct) for l in layers])
+        larr = (C.POINTER(nat.EqdLayer) * len(layers))(*[C.pointer(l.struct) for l in layers])
         nat.check(lib.eqd_iegmn_forward(g, larr, len(layers), C.byref(head.struct), C.byref(io), nat.ptr(ws),
                                         plan.forward_ws_bytes, st), 'eqd_iegmn_forward')
         kab = lambda mask: nat.check(lib.eqd_kabsch_apply(

@@ -333,7 +333,7 @@ class TrainEngine:
                                                nat.ptr(ws.vec), C.byref(nparts), st), 'eqd_bwd_node_mlp')
                 self._reduce(ws.vec, nparts.value, 144, tp.maps['nodevec'], flat, st)
                 # node MLP weight gradients
-                sk = float(lp_obj.struct.skip_weight_h) if dh == nat.HID else 1.0
+                sk = float(lp_obj.struct.dev.skip_weight_h) if dh == nat.HID else 1.0
                 nch = self._tn(ws, ws.n5, dhp, dhp, dh_cur, 64, 64, N, sk, True, st)
                 self._reduce(ws.partial, nch, dhp * 64, tp.maps['node2'], flat, st)
                 self._reduce(ws.colsum, nch, 64, tp.maps['node2_bias'], flat, st)
@@ -361,7 +361,7 @@ class TrainEngine:
                 self._reduce(ws.partial, nch, 64 * 64, tp.maps['edge3'], flat, st)
                 self._reduce(ws.colsum, nch, 64, tp.maps['edge3_bias'], flat, st)
                 nat.check(lib.eqd_bwd_edge_gather(g, nat.ptr(ws.out_ptr), nat.ptr(ws.out_edge), nat.ptr(ws.dz1),
-                                                  nat.ptr(ws.dxrel), nat.ptr(dx_cur), float(lp_obj.struct.x_connection_init),
+                                                  nat.ptr(ws.dxrel), nat.ptr(dx_cur), float(lp_obj.struct.dev.x_connection_init),
                                                   nat.ptr(ws.dP), pw, nat.ptr(dx_nxt), st), 'eqd_bwd_edge_gather')
                 if capture is not None:
                     rows = lambda t, w, n=N: t.reshape(-1)[:n * w].clone().view(n, w)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define EQD_ABI_VERSION 7
+#define EQD_ABI_VERSION 8
 
 #define EQD_EDGE_FEATS 27     /* input_edge_feats_dim, protein_utils.py:71-86 + :373-389 */
 #define EQD_N_RBF 15          /* all_sigmas_dist = 1.5**s, rigid_docking_model.py:116 */
@@ -106,19 +106,13 @@ typedef struct eqd_layer_params {
    * k-chunk stride 2048 B): msg and the coordinate MLP's hidden layer are both linear in the LayerNorm output.
    * 67584 B, 16B-aligned. */
   const void* w_edge_tc;
-  /* HOST pointer to [5][64] floats: edge_ln_g, edge_ln_b, b_edge2, (coors_mlp.0.weight @ b_edge2 + b_coor1),
-   * w_coor2 (copied into the kernel's constant parameter space at launch). */
-  const float* edge_consts_host;
   /* tensor-core node stage (dh == 64 layers only; NULL for the 69-wide layer 0). Same bf16x3 UMMA panels:
    *   w_node_tc : node_mlp.0.weight padded to [64][272] (K order h | aggr | mu | h0(69) | 0) at base 0, split
    *               34816 B; node_mlp.4.weight [64][64] at base 104448, split 8192 B            (129024 B)
    *   w_proj_tc : this layer's projection [Psrc|Pdst|Q|K|V] as 5 groups x 3 splits x 8192 B   (122880 B)
-   *   node_consts_host : HOST [4][64] = node_mlp.0.bias, node_mlp.3.weight, node_mlp.3.bias, node_mlp.4.bias
-   *   proj_bias_host   : HOST [320]   = b_proj                                                           */
+   * (their biases / LayerNorm vectors travel in eqd_layer_consts, below)                                 */
   const void* w_node_tc;
-  const float* node_consts_host;
   const void* w_proj_tc;
-  const float* proj_bias_host;
   const float* w_node1;       /* [dhp+64+dhp+72][dhp] node_mlp.0.weight^T, row blocks [h | aggr_msg | mu | h0] */
   const float* b_node1;       /* [dhp] */
   const float* node_ln_g;     /* [dhp] node_mlp.3.weight (pad 0) */
@@ -129,6 +123,27 @@ typedef struct eqd_layer_params {
   float x_connection_init;    /* args['x_connection_init'] (:286-292) */
   float leaky_slope;          /* args['leakyrelu_neg_slope'] */
 } eqd_layer_params;
+
+/* Launch-time constants of the tensor-core kernels, BY VALUE in host memory: the launcher copies them into the kernel's
+ * constant parameter space (they are operands of the epilogue FFMAs), so they never live behind a device pointer.
+ *   edge      : edge_mlp.3.weight, edge_mlp.3.bias, edge_mlp.4.bias, (coors_mlp.0.weight @ edge_mlp.4.bias +
+ *               coors_mlp.0.bias), coors_mlp.4.weight
+ *   node      : dh == 64: [4][64] = node_mlp.0.bias, node_mlp.3.weight, node_mlp.3.bias, node_mlp.4.bias;
+ *               dh == 69: [80 + 80 + 80 + 64], the first three zero padded to 80
+ *   proj_bias : [320] = b_proj of the five 64-wide groups (dh == 69: only edge_mlp.0.bias at [64, 128))            */
+typedef struct eqd_layer_consts {
+  float edge[5][64];
+  float node[304];
+  float proj_bias[320];
+} eqd_layer_consts;
+
+/* One IEGMN layer as the entry points take it: a HOST-resident descriptor.  `dev` holds device pointers and scalars only
+ * and is what kernels receive by value (a binding may keep or upload it wholesale); `consts` holds host VALUES.  Entry
+ * points of the fp32 FFMA path and of the backward read `dev` only.                                                 */
+typedef struct eqd_layer {
+  eqd_layer_params dev;
+  eqd_layer_consts consts;
+} eqd_layer;
 
 /* ---- keypoint read-out parameters (IEGMN.__init__ :427-438), reference layouts ------------- */
 typedef struct eqd_head_params {
@@ -160,7 +175,7 @@ int eqd_embed_checked(const eqd_graph* g, const float* emb, const float* res_fea
                       float* h0, double* x64, int32_t* status /* [n_pairs+1] */, void* stream);
 
 /* Node projections for a layer (see eqd_layer_params.w_proj): proj[n][128+3*dhp]. */
-int eqd_project(const eqd_graph* g, const eqd_layer_params* p, const float* h, int32_t ldh,
+int eqd_project(const eqd_graph* g, const eqd_layer* p, const float* h, int32_t ldh,
                 float* proj, void* stream);
 
 /* Edge stage of IEGMN_Layer.forward (:204-237, 263-292): RBF, edge MLP, coordinate MLP, mean
@@ -168,19 +183,19 @@ int eqd_project(const eqd_graph* g, const eqd_layer_params* p, const float* h, i
  *   aggr[n][64] = mean_e msg_e ;  x_out[n] = eta*x_orig[n] + (1-eta)*x_in[n] + mean_e x_rel*phi
  * Runs on tcgen05 tensor cores (bf16x3 operand split, fp32 accumulation in TMEM).  he_lig / he_rec must be
  * 16-byte aligned and readable up to the next 16-byte boundary past their end (TMA bulk copies).          */
-int eqd_edge_stage(const eqd_graph* g, const eqd_layer_params* p, const float* proj,
+int eqd_edge_stage(const eqd_graph* g, const eqd_layer* p, const float* proj,
                    const double* x_in, const double* x_orig, float* aggr, double* x_out,
                    int32_t* status /* [n_pairs+1] */, void* stream);
 
 /* Same contract on the fp32 CUDA cores (FFMA); kept as the validation twin of the tensor-core kernel. */
-int eqd_edge_stage_ffma(const eqd_graph* g, const eqd_layer_params* p, const float* proj,
+int eqd_edge_stage_ffma(const eqd_graph* g, const eqd_layer* p, const float* proj,
                         const double* x_in, const double* x_orig, float* aggr, double* x_out,
                         int32_t* status /* [n_pairs+1] */, void* stream);
 
 /* Node stage (:244-256, 319-349): segmented cross attention mu = softmax(q k^T) v over the partner
  * protein, node MLP + LayerNorm + skip -> h_out[n][64]; if p_next != NULL also the next layer's
  * projections (fused eqd_project on h_out) into proj_next.                                    */
-int eqd_node_stage(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next,
+int eqd_node_stage(const eqd_graph* g, const eqd_layer* p, const eqd_layer* p_next,
                    const float* h_in, int32_t ldh, const float* h0, const float* proj,
                    const float* aggr, float* h_out, float* proj_next, void* stream);
 
@@ -190,14 +205,14 @@ int eqd_node_stage(const eqd_graph* g, const eqd_layer_params* p, const eqd_laye
 size_t eqd_kv_blocks_bytes(int32_t n_nodes);
 /* proj[n][320] = [Psrc|Pdst|Q|K|V](h[n]) for a dh==64 layer.  With kv != NULL, K and V are written ONLY as
  * bf16x3 blocks into kv and the fp32 columns 192..319 of proj are left untouched (nothing downstream reads them). */
-int eqd_project_tc(const eqd_graph* g, const eqd_layer_params* p, const float* h /*[n][64]*/, float* proj,
+int eqd_project_tc(const eqd_graph* g, const eqd_layer* p, const float* h /*[n][64]*/, float* proj,
                    void* kv, void* stream);
 /* The same for the 69-wide layer 0 (h = h0 [n][72], K padded to 80): proj[n][344] gets Psrc | Pdst | Q[0:64] at
  * columns 0 / 64 / 128 (the positions the fp32 layer-0 layout uses); K[0:64], V[0:64] go to kv as bf16x3 blocks;
  * channels 64..68 of K, V, Q go to x5[n][16] = [K64..67 | V64..67 | K68 V68 | Q64..68 | 0] (fp32), which is what
  * eqd_attention_tc0 adds to the 64-wide tensor-core products.  kv and x5 are required; x5 must have
  * 8 * (ceil(n / 8) + 8) rows, the rows past n zero (attention reads whole 64-key chunks).                     */
-int eqd_project_tc0(const eqd_graph* g, const eqd_layer_params* p, const float* h0 /*[n][72]*/, float* proj /*[n][344]*/,
+int eqd_project_tc0(const eqd_graph* g, const eqd_layer* p, const float* h0 /*[n][72]*/, float* proj /*[n][344]*/,
                     void* kv, float* x5 /*[n][16]*/, void* stream);
 /* K/V blocks from the fp32 columns of an existing projection buffer (row stride pw floats). */
 int eqd_kv_blocks(const eqd_graph* g, const float* proj, int32_t pw, int32_t koff, int32_t voff, void* kv,
@@ -205,12 +220,12 @@ int eqd_kv_blocks(const eqd_graph* g, const float* proj, int32_t pw, int32_t kof
 /* mu[n][64] = softmax_j(q_n . k_j) v_j over the partner protein (:46-64, 247-256); proj row stride 320. */
 int eqd_attention_tc(const eqd_graph* g, const float* proj, const void* kv, float* mu, void* stream);
 /* h_out = skip(node_mlp([h | aggr | mu | h0])) (:319-337). */
-int eqd_node_mlp_tc(const eqd_graph* g, const eqd_layer_params* p, const float* h_in, const float* aggr,
+int eqd_node_mlp_tc(const eqd_graph* g, const eqd_layer* p, const float* h_in, const float* aggr,
                     const float* mu, const float* h0, float* h_out, void* stream);
 /* Node stage of a dh==64 layer on the tensor cores = attention + node MLP (+ the next layer's projections and
  * K/V blocks when p_next != NULL).  kv holds this layer's K/V blocks on entry, the next layer's on exit;
  * mu is [n][64] scratch.                                                                                   */
-int eqd_node_stage_tc(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next,
+int eqd_node_stage_tc(const eqd_graph* g, const eqd_layer* p, const eqd_layer* p_next,
                       const float* h_in, const float* h0, const float* proj, const float* aggr, void* kv,
                       float* mu, float* h_out, float* proj_next, void* stream);
 
@@ -219,23 +234,23 @@ int eqd_node_stage_tc(const eqd_graph* g, const eqd_layer_params* p, const eqd_l
  *               then one [16][80] group (rows K64..67, V64..67, K68, V68, Q64..68, 0) x 3 splits x 2560 B    (161280 B)
  *   w_node_tc : node_mlp.0.weight with the h and h0 blocks folded (h = h0 in layer 0), [80][224] = 69 -> 80 outputs over
  *               K = [h0 80 | aggr 64 | mu 80], 3 splits x 35840 B; node_mlp.4.weight as [64][80] at 107520    (138240 B)
- *   node_consts_host : HOST [80 + 80 + 80 + 64] = node_mlp.0.bias, node_mlp.3.weight, node_mlp.3.bias (zero padded),
- *               node_mlp.4.bias;   proj_bias_host : HOST [320], edge_mlp.0.bias at [64, 128).
+ *   consts.node = [80 + 80 + 80 + 64] (node_mlp.0.bias, node_mlp.3.weight, node_mlp.3.bias zero padded, node_mlp.4.bias);
+ *   consts.proj_bias = [320] with edge_mlp.0.bias at [64, 128).
  * eqd_attention_tc0: mu[n][72] = softmax(q k^T) v over the partner protein with d = 69: channels 0..63 on the tensor cores
  * from proj[n][344] (Q at column 128) and kv, channels 64..68 in fp32 from x5; columns 69..71 of mu are written as 0.
  * eqd_node_mlp_tc0: h_out[n][64] = node_mlp([h0 | aggr | mu | h0]) without skip connection (:332).
  * eqd_node_stage_tc0 = attention + node MLP + (p_next != NULL) the 64-wide projections of layer 1.              */
 int eqd_attention_tc0(const eqd_graph* g, const float* proj /*[n][344]*/, const void* kv, const float* x5 /*[n+72][16]*/,
                       float* mu /*[n][72]*/, void* stream);
-int eqd_node_mlp_tc0(const eqd_graph* g, const eqd_layer_params* p, const float* h0 /*[n][72]*/, const float* aggr,
+int eqd_node_mlp_tc0(const eqd_graph* g, const eqd_layer* p, const float* h0 /*[n][72]*/, const float* aggr,
                      const float* mu /*[n][72]*/, float* h_out /*[n][64]*/, void* stream);
-int eqd_node_stage_tc0(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next, const float* h0,
+int eqd_node_stage_tc0(const eqd_graph* g, const eqd_layer* p, const eqd_layer* p_next, const float* h0,
                        const float* proj, const float* aggr, void* kv, const float* x5, float* mu, float* h_out,
                        float* proj_next, void* stream);
 
 /* One whole IEGMN_Layer.forward = eqd_edge_stage + eqd_node_stage (proj must hold this layer's
  * projections on entry; holds the next layer's on exit when p_next != NULL).                  */
-int eqd_iegmn_layer_forward(const eqd_graph* g, const eqd_layer_params* p, const eqd_layer_params* p_next,
+int eqd_iegmn_layer_forward(const eqd_graph* g, const eqd_layer* p, const eqd_layer* p_next,
                             const float* h_in, int32_t ldh, const float* h0,
                             const double* x_in, const double* x_orig,
                             float* proj, float* proj_next, float* aggr,
@@ -305,7 +320,7 @@ size_t eqd_forward_stash_bytes(const eqd_graph* g, int32_t n_layers);
  * input coordinates) | h[l] [n][64] f32, l >= 1 (offset, stride) | aggr[l] [n][64] f32 (offset, stride) | mu[l] f32, row
  * stride 72 for the 69-wide layer 0 and 64 otherwise (offset, stride) */
 int eqd_forward_stash_offsets(const eqd_graph* g, int32_t n_layers, size_t* out);
-int eqd_iegmn_forward(const eqd_graph* g, const eqd_layer_params* const* layers, int32_t n_layers,
+int eqd_iegmn_forward(const eqd_graph* g, const eqd_layer* const* layers, int32_t n_layers,
                       const eqd_head_params* hp, const eqd_forward_io* io, void* workspace, size_t workspace_bytes,
                       void* stream);
 
@@ -336,20 +351,20 @@ int eqd_grad_reduce(const float* partial, int32_t nchunks, int64_t stride, const
  * ldmu.  Outputs: dh_in [n][dhp] (overwritten: skip path + h block), daggr [n][64], dmu [n][dhp], dh0_acc [n][72]
  * (accumulated), n5_out / du_out [n][dhp] (operands of the weight-gradient reductions), vec_partial
  * [n_partials][144] = per-CTA partials of {d node_mlp.3.weight [72], d node_mlp.3.bias [72]}.                          */
-int eqd_bwd_node_mlp(const eqd_graph* g, const eqd_layer_params* p, const float* w_node1_lin, const float* w_node2_lin,
+int eqd_bwd_node_mlp(const eqd_graph* g, const eqd_layer* p, const float* w_node1_lin, const float* w_node2_lin,
                      const float* h_in, int32_t ldh, const float* aggr, const float* mu, int32_t ldmu, const float* h0,
                      const float* dh_out, float* dh_in, float* daggr, float* dmu, float* dh0_acc, float* n5_out,
                      float* du_out, float* vec_partial /* [148][144] */, int32_t* n_partials_out, void* stream);
 /* Cross attention backward (:46-64, 247-256): dmu [n][dhp] -> dP[:, 128:] = [dQpre | dKpre | dV] of the combined
  * projection-gradient matrix dP [n][128 + 3 dhp].  proj = this layer's fp32 projections (eqd_project), mu the stashed
  * attention output, rowstat [n][4] scratch.                                                                         */
-int eqd_bwd_attention(const eqd_graph* g, const eqd_layer_params* p, const float* proj, const float* mu, int32_t ldmu,
+int eqd_bwd_attention(const eqd_graph* g, const eqd_layer* p, const float* proj, const float* mu, int32_t ldmu,
                       const float* dmu, float* dP, float* rowstat, void* stream);
 /* Edge stage backward (:204-237, 263-292).  w2lin / w3lin = edge_mlp.4.weight / coors_mlp.0.weight [64][64] as in the
  * state_dict.  Outputs per edge: ein [E][44] = [he | rbf | 0 0], n1, msg, dz3, dmsg, dz1 [E][64], dxrel [E][3] (fp64);
  * vec_partial [n_partials][256] = per-CTA partials {d edge_mlp.3.weight [64], d edge_mlp.3.bias [64],
  * d coors_mlp.4.weight [64], d coors_mlp.4.bias [1]}.                                                                */
-int eqd_bwd_edge(const eqd_graph* g, const eqd_layer_params* p, const float* w2lin, const float* w3lin, const float* proj,
+int eqd_bwd_edge(const eqd_graph* g, const eqd_layer* p, const float* w2lin, const float* w3lin, const float* proj,
                  const double* x_in, const float* daggr, const double* dx_out, float* ein_out, float* n1_out,
                  float* msg_out, float* dz3_out, float* dmsg_out, float* dz1_out, double* dxrel_out,
                  float* vec_partial /* [148][256] */, int32_t* n_partials_out, void* stream);
@@ -359,7 +374,7 @@ int eqd_bwd_edge_gather(const eqd_graph* g, const int32_t* out_ptr, const int32_
                         const double* dxrel, const double* dx_out, float eta, float* dP, int32_t ldp, double* dx_in,
                         void* stream);
 /* dh[n][0:dhp] += dP[n][:] . Wproj^T;  w_projT = eqd_layer_params.w_proj transposed, [128 + 3 dhp][dhp].            */
-int eqd_bwd_project(const eqd_graph* g, const eqd_layer_params* p, const float* w_projT, const float* dP, float* dh,
+int eqd_bwd_project(const eqd_graph* g, const eqd_layer* p, const float* w_projT, const float* dP, float* dh,
                     void* stream);
 /* d residue_emb_layer.weight [21][64] += sum over nodes of that residue type of (dh0_acc + dh_layer0)[0:64].         */
 int eqd_bwd_embed(const eqd_graph* g, const float* res_lig, const float* res_rec, const float* dh0_acc,

@@ -43,9 +43,12 @@ def test_struct_layouts_are_natural_c_layouts():
     assert ctypes.sizeof(nat.EqdGraph) == 24 + 6 * 8 + 8 + 8
     assert nat.EqdGraph.seg_ptr.offset == 24 and nat.EqdGraph.node_tiles.offset == 80
     assert nat.EqdLayerParams.w_proj.offset == 8 and nat.EqdLayerParams.b_coor2.offset == 8 + 10 * 8
-    assert nat.EqdLayerParams.w_edge_tc.offset == 96 and nat.EqdLayerParams.edge_consts_host.offset == 104
-    assert nat.EqdLayerParams.w_node_tc.offset == 112 and nat.EqdLayerParams.proj_bias_host.offset == 136
-    assert nat.EqdLayerParams.w_node1.offset == 144
+    assert nat.EqdLayerParams.w_edge_tc.offset == 96 and nat.EqdLayerParams.w_node_tc.offset == 104
+    assert nat.EqdLayerParams.w_proj_tc.offset == 112 and nat.EqdLayerParams.w_node1.offset == 120
+    # eqd_layer = device part first (a binding may upload / keep it wholesale), host constants BY VALUE after it
+    assert nat.EqdLayer.dev.offset == 0 and nat.EqdLayer.consts.offset == ctypes.sizeof(nat.EqdLayerParams)
+    assert ctypes.sizeof(nat.EqdLayerConsts) == (5 * 64 + 304 + 320) * 4
+    assert not any(n.endswith('_host') for n, _ in nat.EqdLayerParams._fields_)
     assert ctypes.sizeof(nat.EqdHeadParams) == 5 * 8 + 8
     assert nat.EqdHeadParams.m_qk.offset == 32 and nat.EqdHeadParams.leaky_slope.offset == 40
     assert ctypes.sizeof(nat.EqdForwardIO) == 18 * 8 + 8 + 16 and nat.EqdForwardIO.stage_events.offset == 17 * 8
@@ -63,12 +66,13 @@ def _header_struct_fields(name):
         if not decl:
             continue
         for part in decl.split(','):
-            fields.append(re.findall(r'(\w+)\s*$', part.strip())[0])
+            fields.append(re.findall(r'(\w+)\s*$', re.sub(r'(\[\d+\])+\s*$', '', part.strip()))[0])   # name, array extents dropped
     return fields
 
 
 @pytest.mark.parametrize('cname,ctype', [('eqd_graph', nat.EqdGraph), ('eqd_layer_params', nat.EqdLayerParams),
-                                         ('eqd_head_params', nat.EqdHeadParams), ('eqd_forward_io', nat.EqdForwardIO)])
+                                         ('eqd_head_params', nat.EqdHeadParams), ('eqd_forward_io', nat.EqdForwardIO),
+                                         ('eqd_layer_consts', nat.EqdLayerConsts), ('eqd_layer', nat.EqdLayer)])
 def test_ctypes_structs_list_the_header_fields_in_order(cname, ctype):
     assert _header_struct_fields(cname) == [f[0] for f in ctype._fields_]
 

@@ -308,8 +308,8 @@ def test_c_abi_rejects_bad_arguments(cuda_device):
     lib = nat.load()
     g = nat.EqdGraph()
     assert lib.eqd_embed(None, None, None, None, None, None, None, None, None, None, None) == -1
-    lp = nat.EqdLayerParams()
-    lp.dh, lp.dhp = 48, 48
+    lp = nat.EqdLayer()
+    lp.dev.dh, lp.dev.dhp = 48, 48
     one = torch.zeros(8, device=cuda_device)
     assert lib.eqd_project(C.byref(g), C.byref(lp), nat.ptr(one), 48, nat.ptr(one), None) == -2
     g.max_in_degree = 500
