@@ -113,13 +113,11 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     off_l = off_r = 0;
     n_l = 0;
     if (ne <= EQD_TM) {
-      if (half == 0) {
-        if (r < ne) {
-          cp_async4(&W.src[buf][r], g.col_src + e0 + r);
-          cp_async4(&W.dst[buf][r], g.edge_dst + e0 + r);
-        }
-        if (r <= nn) cp_async4(&W.rp[buf][r], g.row_ptr + n0 + r);
+      if (r < ne) {   // every thread fetches the index its own prefetch_x() reads (no barrier in between)
+        if (half == 0) cp_async4(&W.src[buf][r], g.col_src + e0 + r);
+        else cp_async4(&W.dst[buf][r], g.edge_dst + e0 + r);
       }
+      if (half == 0 && r <= nn) cp_async4(&W.rp[buf][r], g.row_ptr + n0 + r);
       // he rows: [e0, e1) split at the ligand/receptor array boundary; 16-byte aligned bulk copies
       const int el0 = min(e0, g.n_lig_edges), el1 = min(e1, g.n_lig_edges);
       n_l = el1 - el0;
@@ -224,7 +222,7 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) a1v[k] = valid ? hrow[24 + k] : 0.f;
-        const float nd2 = -(float)(rx * rx + ry * ry + rz * rz);  // :208-209
+        const float nd2 = valid ? -(float)(rx * rx + ry * ry + rz * rz) : -INFINITY;  // :208-209; padding rows: exp2(-inf) = 0
         // exp(-d^2 / 1.5^q) :210 as ex2.approx(-d^2 * log2(e)/1.5^q): 2 instructions per RBF instead of ~20; the
         // features are <= 1 and the absolute error (<= 2e-7: 2^-22 of ex2 + the rounded scale factor) is below the
         // bf16x3 operand resolution of the GEMM they feed
@@ -233,7 +231,7 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
                                           194.6195068359375, 291.92926025390625};
 #pragma unroll
         for (int j = 0; j < EQD_N_RBF; ++j)
-          a1v[3 + j] = valid ? exp2f(nd2 * (float)(1.4426950408889634 / kS[j])) : 0.f;
+          a1v[3 + j] = exp2f(nd2 * (float)(1.4426950408889634 / kS[j]));
 #pragma unroll
         for (int k = 18; k < 24; ++k) a1v[k] = 0.f;
       }
@@ -322,6 +320,13 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&S.a_bar[wg]);
+    if (has_next) {
+      // The next tile's x[src] / x[dst] gathers go out here, two GEMMs before they are needed (issued in the tail of the tile
+      // their latency sat in front of the next tile's first barrier).  xs of this tile was consumed in S0 by the half-1 thread of my row, which has since met me at the LayerNorm pair
+      // barrier; my own index of the next tile (fetched behind GEMM1) has landed once my copy groups drain
+      cp_async_wait<0>();
+      prefetch_x(buf ^ 1, nen);
+    }
     // ---- GEMM2 and GEMM3 on the same A operand ------------------------------------------------------------------
     // msg = W2 a1 + b2 (edge_mlp.4) and the coordinate MLP's hidden pre-activation W3 msg + b3 =
     // (W3 W2) a1 + (W3 b2 + b3) are both linear in a1: the stacked panel [W2 ; W3 W2] gives them from one A operand
@@ -351,6 +356,40 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
       }
       __syncwarp();
     }
+    // mean aggregation of msg at the destination nodes (:280-283): 4 threads per channel, each a run of nodes
+    auto aggregate = [&](bool deg10) {
+      const int c = q & 63, part = q >> 6;
+      const float* col = W.stage + c;
+      if (deg10) {  // same sums, no row_ptr lookups
+        int nd = (nn * part) >> 2, nd1 = (nn * (part + 1)) >> 2;
+        if (nn * 3 <= 64) {   // threads 192..255 hold the coordinate update: the other three quarters share the nodes
+          nd = (nn * part) / 3;
+          nd1 = part < 3 ? (nn * (part + 1)) / 3 : nd;
+        }
+        for (; nd < nd1; ++nd) {
+          const float* cr = col + nd * 10 * TC_LD;
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 10; j += 2) {
+            s0 += cr[j * TC_LD];
+            s1 += cr[(j + 1) * TC_LD];
+          }
+          aggr[(long)(n0 + nd) * 64 + c] = (s0 + s1) / 10.f;
+        }
+      } else {
+        for (int nd = (nn * part) >> 2, nd1 = (nn * (part + 1)) >> 2; nd < nd1; ++nd) {
+          const int rs = W.rp[buf][nd] - e0, re = W.rp[buf][nd + 1] - e0;
+          float s0 = 0.f, s1 = 0.f;
+          int rr = rs;
+          for (; rr + 1 < re; rr += 2) {
+            s0 += col[rr * TC_LD];
+            s1 += col[(rr + 1) * TC_LD];
+          }
+          if (rr < re) s0 += col[rr * TC_LD];
+          aggr[(long)(n0 + nd) * 64 + c] = re > rs ? (s0 + s1) / (float)(re - rs) : 0.f;
+        }
+      }
+    };
     if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, tile, 12);
     mbar_wait(&S.mma_bar[wg], mma_phase);
     mma_phase ^= 1;
@@ -377,38 +416,36 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
     }
     cp_async_wait<0>();  // next tile's indices have landed (issued behind GEMM1)
     tc_fence_before();
-    wg_barrier(wg);      // msg tile, phi halves, x_rel complete; next tile's indices visible
+    // msg tile, phi halves, x_rel complete; next tile's indices visible.  The barrier also tells whether every node of the tile
+    // has exactly 10 in-edges (the k-NN graphs of protein_utils.py:339-346): the tail then runs without row_ptr lookups.
+    const bool deg10 = wg_barrier_and(wg, q >= nn || W.rp[buf][q + 1] - W.rp[buf][q] == 10);
     if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, tile, 15);
-    if (has_next) prefetch_x(buf ^ 1, nen);  // its x[src], x[dst]: xs of this tile was consumed in S1
-    for (int o = q; o < nn * 3; o += 256) {  // coordinate update :264, 274-277, 286-292
+    // coordinate update :264, 274-277, 286-292 on the LAST threads of the group (warp 0 also issues the MMAs; the threads
+    // 192..255 take no aggregation work below when all 3 nn outputs fit there)
+    for (int o = 255 - q; o < nn * 3; o += 256) {
       int nd = o / 3, comp = o - nd * 3;
       int rs = W.rp[buf][nd] - e0, re = W.rp[buf][nd + 1] - e0;
+      long gi = (long)(n0 + nd) * 3 + comp;
+      const double xo_ = x_orig[gi], xi_ = x_in[gi];   // issued before the phi sums, consumed after them
       double sum = 0.0;
+      if (deg10) {   // fixed in-degree: the same fused multiply-add chain, unrolled (its shared loads go out together)
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          const int rr = nd * 10 + j;
+          const double ph = W.red[rr * 2] + W.red[rr * 2 + 1] + (double)p.b_coor2;
+          sum += W.xm[rr * 3 + comp] * ph;
+        }
+      } else
       for (int rr = rs; rr < re; ++rr) {
         const double ph = W.red[rr * 2] + W.red[rr * 2 + 1] + (double)p.b_coor2;
         sum += W.xm[rr * 3 + comp] * ph;  // x_rel * phi :264
       }
       int deg = re - rs;
       double upd = deg > 0 ? sum / (double)deg : 0.0;
-      long gi = (long)(n0 + nd) * 3 + comp;
       double eta = (double)p.x_connection_init;
-      x_out[gi] = eta * x_orig[gi] + (1.0 - eta) * x_in[gi] + upd;
+      x_out[gi] = eta * xo_ + (1.0 - eta) * xi_ + upd;
     }
-    {  // mean aggregation of msg at the destination nodes (:280-283): 4 threads per channel, each a run of nodes
-      const int c = q & 63, part = q >> 6;
-      const float* col = W.stage + c;
-      for (int nd = (nn * part) >> 2, nd1 = (nn * (part + 1)) >> 2; nd < nd1; ++nd) {
-        const int rs = W.rp[buf][nd] - e0, re = W.rp[buf][nd + 1] - e0;
-        float s0 = 0.f, s1 = 0.f;
-        int rr = rs;
-        for (; rr + 1 < re; rr += 2) {
-          s0 += col[rr * TC_LD];
-          s1 += col[(rr + 1) * TC_LD];
-        }
-        if (rr < re) s0 += col[rr * TC_LD];
-        aggr[(long)(n0 + nd) * 64 + c] = re > rs ? (s0 + s1) / (float)(re - rs) : 0.f;
-      }
-    }
+    aggregate(deg10);
     e0 = e0n; ne = nen; off_l = off_ln; n_l = n_ln; off_r = off_rn; buf ^= 1;
   }
   if (q == 0) TRACE_PHASE(0, blockIdx.x * 2 + wg, 0xffff, 16);

@@ -49,6 +49,16 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
 // barrier among the 256 threads of one tile group (named barriers 1, 2)
 __device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 256;" ::"r"(wg + 1) : "memory"); }
 // barrier between the two warps that own the two column halves of the same 32 rows (named barriers 3..10)
+// group barrier + AND-reduction of a predicate over its 256 threads
+__device__ __forceinline__ bool wg_barrier_and(int wg, bool pred) {
+  unsigned r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.and.pred q, %2, 256, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+      : "=r"(r)
+      : "r"((unsigned)pred), "r"(wg + 1)
+      : "memory");
+  return r != 0;
+}
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
