@@ -13,6 +13,14 @@
 
 namespace eqd {
 
+// -DATTN_PROF: thread 0 of CTA 0 accumulates the SM cycles it spends in each phase of the tile loop (scripts/attn_variants.py)
+#ifdef ATTN_PROF
+__device__ long long g_attn_prof[16];
+#define PROF_MARK(k) do { if (tid == 0 && blockIdx.x == 0) { const long long t_ = clock64(); prof_acc[k] += t_ - prof_t; prof_t = t_; } } while (0)
+#else
+#define PROF_MARK(k) do { } while (0)
+#endif
+
 #define AT_THREADS 512
 #define AT_KEYS 64            // keys per chunk = 8 blocks
 #define AT_CHUNK_BYTES 8192   // per split
@@ -147,7 +155,14 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
     tc_fence_after();
   };
 
+#ifdef ATTN_PROF
+  __shared__ long long prof_acc[16];
+  long long prof_t = clock64();
+  if (tid == 0)
+    for (int k = 0; k < 16; ++k) prof_acc[k] = 0;
+#endif
   for (int tile = blockIdx.x * 2 + wg; tile < g.n_node_tiles; tile += gridDim.x * 2) {
+    PROF_MARK(15);
     if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, tile, 1);
     const int seg = g.node_tiles[2 * tile], node0 = g.node_tiles[2 * tile + 1];
     const int nvalid = min(EQD_TM, g.seg_ptr[seg + 1] - node0);
@@ -157,6 +172,7 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
     const int nchunks = (blk_hi - blk_lo + 7) >> 3;
     const int node = node0 + r;
     const bool valid = r < nvalid;
+    PROF_MARK(0);   // tile metadata (dependent global loads)
     if (nchunks > 0) load_chunk(k_g, G.k[0], &S.k_bar[wg][0], blk_lo, 0);
     float q5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     if (X5 && valid) {
@@ -175,6 +191,7 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
     }
     tc_fence_before();
     wg_barrier(wg);
+    PROF_MARK(1);   // Q row -> TMEM + barrier
     // ---------------- pass 1: row maxima ----------------------------------------------------------------
     float mx = -INFINITY;
     for (int c = 0; c < nchunks; ++c) {
@@ -182,12 +199,14 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
       if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, tile, (c << 4) | 2);
       mbar_wait(&S.k_bar[wg][kb_], kph[kb_]);
       kph[kb_] ^= 1;
+      PROF_MARK(2);   // pass 1: K chunk wait
       issue_s(kb_, true);
       // the other K buffer was last read by the S GEMM of chunk c-1, already waited for: prefetch into it
       if (c + 1 < nchunks) load_chunk(k_g, G.k[kb_ ^ 1], &S.k_bar[wg][kb_ ^ 1], blk_lo + 8 * (c + 1), kb_ ^ 1);
       else load_chunk(k_g, G.k[kb_ ^ 1], &S.k_bar[wg][kb_ ^ 1], blk_lo, kb_ ^ 1);   // first chunk of pass 2
       if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, tile, (c << 4) | 3);
       wait_mma();
+      PROF_MARK(3);   // pass 1: issue + S(hi) MMA wait
       float s[32];
       tmem_ld32f(tmem + 96 + half * 32, s);
       if (X5) add_s5(s, G.x5c[kb_], q5);
@@ -199,6 +218,7 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
       }
       tc_fence_before();
       wg_barrier(wg);  // S drained before the next S GEMM overwrites it
+      PROF_MARK(4);   // pass 1: ld + max + barrier
     }
     G.red[r * 2 + half] = mx;
     wg_barrier(wg);
@@ -215,6 +235,7 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
       if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, tile, (c << 4) | 4);
       mbar_wait(&S.k_bar[wg][kb_], kph[kb_]);
       kph[kb_] ^= 1;
+      PROF_MARK(5);   // pass 2: K chunk wait (+ row-max exchange on the first chunk)
       issue_s(kb_, false);
       if (c + 1 < nchunks) {
         load_chunk(k_g, G.k[kb_ ^ 1], &S.k_bar[wg][kb_ ^ 1], blk_lo + 8 * (c + 1), kb_ ^ 1);
@@ -222,6 +243,7 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
       }
       if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, tile, (c << 4) | 5);
       wait_mma();
+      PROF_MARK(6);   // pass 2: issue + S MMA wait
       float s[32];
       tmem_ld32f(tmem + 96 + half * 32, s);
       if (X5) add_s5(s, G.x5c[kb_], q5);
@@ -245,16 +267,20 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
       }
       l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
       tc_fence_before();
+      PROF_MARK(7);   // pass 2: ld + exp
       wg_barrier(wg);  // every S value is in registers: the P splits may overwrite the S columns
+      PROF_MARK(8);   // pass 2: barrier 1
       store_half_split3(tmem + 96 + half * 16, s);
       tc_fence_before();
       wg_barrier(wg);
+      PROF_MARK(9);   // pass 2: P split/store + barrier 2
       if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, tile, (c << 4) | 6);
       mbar_wait(&S.v_bar[wg][vb_], vph[vb_]);
       vph[vb_] ^= 1;
       issue_pv(vb_, 0u);
       if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, tile, (c << 4) | 7);
       wait_mma();      // P (= the S region) and this V buffer are free again
+      PROF_MARK(10);  // pass 2: V wait + issue + P.V MMA wait
       // The tensor core truncates (round-toward-zero) every time it adds into an fp32 accumulator, a systematic
       // bias that grows with the number of accumulation steps; each 64-key chunk is therefore accumulated on its
       // own (4 full-magnitude steps) and the chunks are summed here with round-to-nearest FADDs.
@@ -270,6 +296,7 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
       // flips look like none -- and spin forever.  (This was a real, rare hang: ~1 in 10^4 launches back to back.)
       tc_fence_before();
       wg_barrier(wg);
+      PROF_MARK(11);  // pass 2: O ld + accumulate + barrier 3
     }
     // ---------------- mu = O / l -----------------------------------------------------------------------------
     G.red[r * 2 + half] = l;
@@ -299,7 +326,12 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
     }
     tc_fence_before();
     wg_barrier(wg);
+    PROF_MARK(12);  // mu = O / l, stores, barrier
   }
+#ifdef ATTN_PROF
+  if (tid == 0 && blockIdx.x == 0)
+    for (int k = 0; k < 16; ++k) g_attn_prof[k] = prof_acc[k];
+#endif
   if (q == 0) TRACE_PHASE(1, blockIdx.x * 2 + wg, 0xffff, 15);
   tc_fence_before();
   __syncthreads();
@@ -310,6 +342,12 @@ attention_tc_kernel(eqd_graph g, const float* __restrict__ proj, int pw, const u
 }  // namespace eqd
 
 EQD_TRACE_SETTER(eqd_trace_set_attn)
+
+#ifdef ATTN_PROF
+extern "C" int eqd_attn_prof_read(long long* out16) {
+  return (int)cudaMemcpyFromSymbol(out16, eqd::g_attn_prof, sizeof(long long) * 16);
+}
+#endif
 
 template <bool X5>
 static int launch_attention_tc(const eqd_graph* g, const float* proj, int pw, const void* kv, const float* x5, float* mu,

@@ -146,11 +146,12 @@ __device__ __forceinline__ unsigned cvt_bf16x2(float hi, float lo) {
 // (v0, v1) -> three packed bf16x2 words (v0 in the low half = even k)
 __device__ __forceinline__ void split3_pair(float v0, float v1, unsigned& p0, unsigned& p1, unsigned& p2) {
   p0 = cvt_bf16x2(v1, v0);
-  float r0 = v0 - __uint_as_float(p0 << 16), r1 = v1 - __uint_as_float(p0 & 0xFFFF0000u);
-  p1 = cvt_bf16x2(r1, r0);
-  r0 -= __uint_as_float(p1 << 16);
-  r1 -= __uint_as_float(p1 & 0xFFFF0000u);
-  p2 = cvt_bf16x2(r1, r0);
+  // v - hi as fma(hi, -1, v) on both lanes at once (fma.f32x2; exact product, same rounding as the subtraction)
+  const float2 m1 = make_float2(-1.f, -1.f);
+  float2 rr = __ffma2_rn(make_float2(__uint_as_float(p0 << 16), __uint_as_float(p0 & 0xFFFF0000u)), m1, make_float2(v0, v1));
+  p1 = cvt_bf16x2(rr.y, rr.x);
+  rr = __ffma2_rn(make_float2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xFFFF0000u)), m1, rr);
+  p2 = cvt_bf16x2(rr.y, rr.x);
 }
 __device__ __forceinline__ void tmem_st16(unsigned taddr, const unsigned (&v)[16]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
