@@ -91,95 +91,172 @@ graph_align_frames_kernel(int n_prot, const int* __restrict__ seg_ptr, const flo
   }
 }
 
-// mean over all atom pairs of |a - b|, outer loop over the atoms of the LOWER-index residue: d(i,j) == d(j,i) bitwise
-__device__ __forceinline__ double mean_atom_distance(const float* __restrict__ A, int na, const float* __restrict__ Bp, int nb) {
-  double s = 0.0;
+// Centroid and mean atom-to-centroid distance of every residue: the bounds of the neighbour search below.
+__global__ void graph_centroid_kernel(int n_nodes, const int* __restrict__ atom_ptr, const float* __restrict__ atoms,
+                                      double* __restrict__ cen /*[n][4] = cx, cy, cz, rho*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  const int a0 = atom_ptr[i], na = atom_ptr[i + 1] - a0;
+  double cx = 0.0, cy = 0.0, cz = 0.0;
   for (int a = 0; a < na; ++a) {
+    cx += (double)atoms[(long)(a0 + a) * 3];
+    cy += (double)atoms[(long)(a0 + a) * 3 + 1];
+    cz += (double)atoms[(long)(a0 + a) * 3 + 2];
+  }
+  const double inv = na > 0 ? 1.0 / (double)na : 0.0;
+  cx *= inv; cy *= inv; cz *= inv;
+  double rho = 0.0;
+  for (int a = 0; a < na; ++a) {
+    const double dx = (double)atoms[(long)(a0 + a) * 3] - cx, dy = (double)atoms[(long)(a0 + a) * 3 + 1] - cy,
+                 dz = (double)atoms[(long)(a0 + a) * 3 + 2] - cz;
+    rho += sqrt(dx * dx + dy * dy + dz * dz);
+  }
+  cen[(long)i * 4] = cx; cen[(long)i * 4 + 1] = cy; cen[(long)i * 4 + 2] = cz; cen[(long)i * 4 + 3] = rho * inv;
+}
+
+// Quarter `part` of the sum over all atom pairs of |a - b|: atoms part, part + 4, ... of residue A (the LOWER-index residue of
+// the pair, so that d(i,j) == d(j,i) bitwise) against every atom of B.  The four quarters are added as (s0 + s1) + (s2 + s3).
+__device__ __forceinline__ double atom_distance_sum_part(const float* __restrict__ A, int na, const float* __restrict__ Bp, int nb, int part) {
+  double s = 0.0;
+  for (int a = part; a < na; a += 4) {
     const double ax = A[a * 3], ay = A[a * 3 + 1], az = A[a * 3 + 2];
     for (int b = 0; b < nb; ++b) {
       const double dx = ax - (double)Bp[b * 3], dy = ay - (double)Bp[b * 3 + 1], dz = az - (double)Bp[b * 3 + 2];
       s += sqrt(dx * dx + dy * dy + dz * dz);
     }
   }
-  return s / ((double)na * (double)nb);
+  return s;
 }
 
-// One CTA per destination residue i.  drow (dynamic smem): the distance row of i over its protein.
+// One CTA per destination residue i.  Dynamic smem: drow[n] (lower bound, then the exact distance of the candidates, +inf
+// otherwise) and ub[n] (upper bound; later reused as the candidate list).
+//   The mean all-atom distance D_ij (:324-329, 64 fp64 square roots per residue pair) is only evaluated for residues that can
+//   be among the neighbours.  With c = residue centroid and rho = mean atom-to-centroid distance,
+//     |c_i - c_j|  <=  D_ij  <=  |c_i - c_j| + rho_i + rho_j        (convexity of the norm; triangle inequality)
+//   so when more than K residues are CERTAINLY inside the cutoff (upper bound < cutoff) the K nearest all lie below any
+//   tau that at least K upper bounds stay under (taken from a 64-bin histogram of the upper bounds: within cutoff / 64 of
+//   the K-th smallest), and a residue whose lower bound exceeds tau cannot be selected; otherwise every residue whose
+//   lower bound is inside the cutoff is evaluated.  Selection and output order are those of the reference:
+//   the K closest in ascending distance (:342-343), or all residues inside the cutoff in ascending index (:340).
 __global__ void __launch_bounds__(GB_THREADS)
 graph_knn_kernel(int n_nodes, const int* __restrict__ node_seg, const int* __restrict__ seg_ptr, const int* __restrict__ atom_ptr,
-                 const float* __restrict__ atoms, const double* __restrict__ xa, double cutoff, int max_neighbor,
-                 int* __restrict__ deg, int* __restrict__ nbr /*[n][GB_MAXK]*/, double* __restrict__ nbr_d /*[n][GB_MAXK]*/,
-                 float* __restrict__ mu_r_norm /*[n][5]*/) {
+                 const float* __restrict__ atoms, const double* __restrict__ xa, const double* __restrict__ cen, double cutoff,
+                 int max_neighbor, int* __restrict__ deg, int* __restrict__ nbr /*[n][GB_MAXK]*/,
+                 double* __restrict__ nbr_d /*[n][GB_MAXK]*/, float* __restrict__ mu_r_norm /*[n][5]*/) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  if (i >= n_nodes) return;
+  const int s = node_seg[i], j0 = seg_ptr[s], j1 = seg_ptr[s + 1], n = j1 - j0, ii = i - j0;
   double* drow = reinterpret_cast<double*>(smem_raw);
+  double* ub = drow + n;
+  int* candl = reinterpret_cast<int*>(ub);       // the candidate list reuses the upper-bound row once tau is known
   __shared__ float ai[GB_MAXA * 3];
-  __shared__ double red_v[GB_THREADS];
-  __shared__ int red_i[GB_THREADS];
   __shared__ int sel[GB_MAXK];
   __shared__ double seld[GB_MAXK];
-  __shared__ int count_s;
-  const int i = blockIdx.x, tid = threadIdx.x;
-  if (i >= n_nodes) return;
-  const int s = node_seg[i], j0 = seg_ptr[s], j1 = seg_ptr[s + 1], n = j1 - j0;
+  __shared__ int n_certain, n_cand, n_valid;
+  __shared__ int hist[64];
+  __shared__ double tau_s;
   const int a0 = atom_ptr[i], na = atom_ptr[i + 1] - a0;
   const bool cached = na <= GB_MAXA;
   if (cached)
     for (int o = tid; o < na * 3; o += GB_THREADS) ai[o] = atoms[(long)a0 * 3 + o];
+  if (tid == 0) { n_certain = 0; n_cand = 0; n_valid = 0; tau_s = INFINITY; }
+  if (tid < 64) hist[tid] = 0;
+  const double bin_w = cutoff * (1.0 / 64.0);
+  const double cix = cen[(long)i * 4], ciy = cen[(long)i * 4 + 1], ciz = cen[(long)i * 4 + 2], rhoi = cen[(long)i * 4 + 3];
   __syncthreads();
   const float* Ai = cached ? ai : atoms + (long)a0 * 3;
-  int cnt = 0;
-  for (int jj = tid; jj < n; jj += GB_THREADS) {
-    const int j = j0 + jj;
-    double d = INFINITY;
-    if (j != i) {
-      const int b0 = atom_ptr[j], nb = atom_ptr[j + 1] - b0;
-      d = j > i ? mean_atom_distance(Ai, na, atoms + (long)b0 * 3, nb) : mean_atom_distance(atoms + (long)b0 * 3, nb, Ai, na);
-    }
-    drow[jj] = d;
-    cnt += d < cutoff ? 1 : 0;
-  }
-  red_i[tid] = cnt;
-  __syncthreads();
-  for (int st = GB_THREADS / 2; st > 0; st >>= 1) {
-    if (tid < st) red_i[tid] += red_i[tid + st];
-    __syncthreads();
-  }
-  if (tid == 0) count_s = red_i[0];
-  __syncthreads();
-  const int nvalid = count_s;
-  const bool by_distance = nvalid > max_neighbor;       // (:342-343) the max_neighbor closest, ascending distance;
-  const int k_out = by_distance ? max_neighbor : nvalid;  // otherwise every residue within the cutoff, ascending index (:340)
-  for (int k = 0; k < k_out; ++k) {
-    double bv = INFINITY;
-    int bi = -1;
+  // ---- bounds --------------------------------------------------------------------------------------------------------
+  {
+    int c = 0;
     for (int jj = tid; jj < n; jj += GB_THREADS) {
-      const double d = drow[jj];
-      if (!(d < cutoff)) continue;
-      const double key = by_distance ? d : (double)jj;
-      if (bi < 0 || key < bv) { bv = key; bi = jj; }
-    }
-    red_v[tid] = bv;
-    red_i[tid] = bi;
-    __syncthreads();
-    for (int st = GB_THREADS / 2; st > 0; st >>= 1) {
-      if (tid < st) {
-        const int oi = red_i[tid + st];
-        const double ov = red_v[tid + st];
-        if (oi >= 0 && (red_i[tid] < 0 || ov < red_v[tid] || (ov == red_v[tid] && oi < red_i[tid]))) {
-          red_v[tid] = ov;
-          red_i[tid] = oi;
+      double lo = INFINITY, hi = INFINITY;
+      if (jj != ii) {
+        const double* cj = cen + (long)(j0 + jj) * 4;
+        const double dx = cix - cj[0], dy = ciy - cj[1], dz = ciz - cj[2];
+        lo = sqrt(dx * dx + dy * dy + dz * dz);
+        hi = lo + rhoi + cj[3];
+        if (hi < cutoff) {
+          ++c;
+          atomicAdd(&hist[min(63, (int)(hi / bin_w))], 1);
         }
       }
-      __syncthreads();
+      drow[jj] = lo;
+      ub[jj] = hi;
     }
-    if (tid == 0) {
-      const int jj = red_i[0];
-      sel[k] = j0 + jj;
-      seld[k] = drow[jj];
-      drow[jj] = INFINITY;          // taken
-    }
-    __syncthreads();
+    if (c) atomicAdd(&n_certain, c);
   }
+  __syncthreads();
+  const bool certain = n_certain > max_neighbor;     // more than K residues are inside the cutoff whatever their exact distance
+  if (certain && tid < 32) {   // tau = upper edge of the first histogram bin at which the running count reaches K
+    const int h0 = hist[2 * lane], h1 = hist[2 * lane + 1];
+    int run = h0 + h1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, run, o);
+      if (lane >= o) run += v;
+    }
+    const int before = run - h0 - h1;    // elements in the bins below 2 * lane
+    int b = 64;
+    if (before < max_neighbor && before + h0 >= max_neighbor) b = 2 * lane;
+    else if (before + h0 < max_neighbor && run >= max_neighbor) b = 2 * lane + 1;
+    if (b < 64) tau_s = fmin(cutoff, (double)(b + 1) * bin_w * (1.0 + 1e-12));
+  }
+  __syncthreads();
+  const double thr = certain ? tau_s : cutoff;
+  const double thr_safe = thr + 1e-9 * (1.0 + thr);   // the bounds hold exactly in real arithmetic; fp64 rounding is ~1e-15
+  // ---- candidates -----------------------------------------------------------------------------------------------------
+  for (int jj = tid; jj < n; jj += GB_THREADS) {   // (the upper bounds are dead since the barrier above: the list may overwrite them)
+    if (jj != ii && drow[jj] <= thr_safe) candl[atomicAdd(&n_cand, 1)] = jj;
+    else drow[jj] = INFINITY;
+  }
+  __syncthreads();
+  const int ncand = n_cand;
+  // ---- exact distances: 4 lanes per candidate ------------------------------------------------------------------------------
+  for (int t0 = tid - lane; t0 < ncand * 4; t0 += GB_THREADS) {
+    const int t = t0 + lane;
+    const bool act = t < ncand * 4;
+    double part_sum = 0.0;
+    int jj = 0, nb = 1;
+    if (act) {
+      jj = candl[t >> 2];
+      const int j = j0 + jj, b0 = atom_ptr[j];
+      nb = atom_ptr[j + 1] - b0;
+      const float* Bj = atoms + (long)b0 * 3;
+      part_sum = j > i ? atom_distance_sum_part(Ai, na, Bj, nb, t & 3) : atom_distance_sum_part(Bj, nb, Ai, na, t & 3);
+    }
+    const double o1 = __shfl_xor_sync(0xffffffffu, part_sum, 1);
+    const double s01 = (lane & 1) ? o1 + part_sum : part_sum + o1;        // (s0 + s1) resp. (s2 + s3), same operand order in both lanes
+    const double o2 = __shfl_xor_sync(0xffffffffu, s01, 2);
+    const double tot = (lane & 2) ? o2 + s01 : s01 + o2;                  // (s0 + s1) + (s2 + s3)
+    if (act && (t & 3) == 0) {
+      const double d = tot / ((double)na * (double)nb);
+      drow[jj] = d;
+      if (d < cutoff) atomicAdd(&n_valid, 1);
+    }
+  }
+  __syncthreads();
+  const int nvalid = certain ? max_neighbor + 1 : n_valid;
+  const bool by_distance = nvalid > max_neighbor;       // (:342-343) the max_neighbor closest, ascending distance;
+  const int k_out = by_distance ? max_neighbor : nvalid;  // otherwise every residue within the cutoff, ascending index (:340)
+  // ---- selection: the output slot of a candidate is its rank ---------------------------------------------------------------
+  for (int c = tid; c < ncand; c += GB_THREADS) {
+    const int jj = candl[c];
+    const double d = drow[jj];
+    if (!(d < cutoff)) continue;
+    int rank = 0;
+    for (int q = 0; q < ncand; ++q) {
+      const int jq = candl[q];
+      const double dq = drow[jq];
+      if (!(dq < cutoff)) continue;
+      rank += by_distance ? ((dq < d || (dq == d && jq < jj)) ? 1 : 0) : (jq < jj ? 1 : 0);
+    }
+    if (rank < k_out) {
+      sel[rank] = j0 + jj;
+      seld[rank] = d;
+    }
+  }
+  __syncthreads();
   if (tid < k_out) {
     nbr[(long)i * GB_MAXK + tid] = sel[tid];
     nbr_d[(long)i * GB_MAXK + tid] = seld[tid];
@@ -241,7 +318,7 @@ __global__ void graph_node_seg_kernel(int n_prot, const int* __restrict__ seg_pt
 extern "C" size_t eqd_graph_build_workspace_bytes(int32_t n_nodes) {
   const size_t N = n_nodes > 0 ? n_nodes : 1;
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  return al(N * 3 * 8) + al(N * 9 * 8) + al(N * 4) + al(N * GB_MAXK * 4) + al(N * GB_MAXK * 8);
+  return al(N * 3 * 8) + al(N * 9 * 8) + al(N * 4) + al(N * GB_MAXK * 4) + al(N * GB_MAXK * 8) + al(N * 4 * 8);
 }
 
 // Stage 1: alignment, frames, neighbour search.  Outputs deg [n] (the caller turns it into row_ptr with an exclusive
@@ -254,8 +331,8 @@ extern "C" int eqd_graph_build_knn(int32_t n_prot, int32_t n_nodes, int32_t max_
   if (max_neighbor < 1 || max_neighbor > GB_MAXK || max_protein_nodes < 1) return EQD_ERR_UNSUPPORTED;
   if (workspace_bytes < eqd_graph_build_workspace_bytes(n_nodes)) return EQD_ERR_WORKSPACE;
   if (n_nodes <= 0 || n_prot <= 0) return EQD_OK;
-  const size_t row_bytes = (size_t)max_protein_nodes * sizeof(double);
-  if (row_bytes > 200 * 1024) return EQD_ERR_UNSUPPORTED;      // > 25600 residues in one protein
+  const size_t row_bytes = (size_t)max_protein_nodes * 2 * sizeof(double);   // lower-bound / distance row + upper-bound row
+  if (row_bytes > 200 * 1024) return EQD_ERR_UNSUPPORTED;      // > 12800 residues in one protein
   cudaStream_t st = (cudaStream_t)stream;
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t N = n_nodes;
@@ -265,12 +342,15 @@ extern "C" int eqd_graph_build_knn(int32_t n_prot, int32_t n_nodes, int32_t max_
   int* node_seg = reinterpret_cast<int*>(w + al(N * 3 * 8) + al(N * 9 * 8));
   int* nbr = reinterpret_cast<int*>(w + al(N * 3 * 8) + al(N * 9 * 8) + al(N * 4));
   double* nbr_d = reinterpret_cast<double*>(w + al(N * 3 * 8) + al(N * 9 * 8) + al(N * 4) + al(N * GB_MAXK * 4));
+  double* cen = reinterpret_cast<double*>(w + al(N * 3 * 8) + al(N * 9 * 8) + al(N * 4) + al(N * GB_MAXK * 4) + al(N * GB_MAXK * 8));
+  eqd::graph_centroid_kernel<<<(n_nodes + 127) / 128, 128, 0, st>>>(n_nodes, atom_ptr, atoms, cen);
+  EQD_CUDA_LAUNCH_CHECK();
   eqd::graph_align_frames_kernel<<<n_prot, GB_THREADS, 0, st>>>(n_prot, seg_ptr, nca_c, bound_ca, xa, frames, x);
   EQD_CUDA_LAUNCH_CHECK();
   eqd::graph_node_seg_kernel<<<n_prot, 128, 0, st>>>(n_prot, seg_ptr, node_seg);
   EQD_CUDA_LAUNCH_CHECK();
   EQD_SET_SMEM((eqd::graph_knn_kernel), row_bytes);
-  eqd::graph_knn_kernel<<<n_nodes, GB_THREADS, row_bytes, st>>>(n_nodes, node_seg, seg_ptr, atom_ptr, atoms, xa, (double)cutoff,
+  eqd::graph_knn_kernel<<<n_nodes, GB_THREADS, row_bytes, st>>>(n_nodes, node_seg, seg_ptr, atom_ptr, atoms, xa, cen, (double)cutoff,
                                                               max_neighbor, deg, nbr, nbr_d, mu_r_norm);
   EQD_CUDA_LAUNCH_CHECK();
   return EQD_OK;
