@@ -92,18 +92,20 @@ loss_mse_intersection_kernel(eqd_graph g, const float* __restrict__ pred, const 
 // of the batch).  The cost matrix C (fp64, cap x 50) and the per-sink source lists (int16) live in shared memory when they
 // fit (cap <= 346: both; <= 410: C only; <= 917: lists only), else in global memory (L2); flows x_ik <= 50 are int8.
 struct OtView {
-  double *P, *Y, *u, *ds, *v, *base_v, *Cm;
-  int *excess, *par_s, *exl, *exq, *stamp, *vislist, *deficit, *par_k, *fl_cnt, *base_i;
+  double *P, *Y, *u, *v, *base_v, *Cm;
+  double *Wv, *dsink;          // sink graph: Wv[k][64] = min over the feeders i of sink k of C[i][.] - u[i]; settle distances
+  int *excess, *exl, *exq, *stamp, *deficit, *par_k, *par_via, *fl_cnt, *base_i, *ord;
   signed char* xs;
-  short* fls;
+  short *fls, *Wi;             // Wi[k][64] = the feeder that attains Wv (-1: none)
 };
+#define OT_WLD 64
 struct OtLayout {
   size_t bytes;
   int c_smem, fl_smem;
 };
 __host__ __device__ inline OtLayout ot_layout(int cap) {
-  const size_t fixed = (size_t)(cap * 6 + EQD_HEADS * 6 + 2 * cap + 2 * EQD_HEADS) * 8 + (size_t)(6 * cap + 4 * EQD_HEADS) * 4 +
-                       (size_t)cap * EQD_HEADS + 256;
+  const size_t fixed = (size_t)(cap * 6 + EQD_HEADS * 6 + cap + 2 * EQD_HEADS + EQD_HEADS * OT_WLD + OT_WLD) * 8 +
+                       (size_t)(4 * cap + 5 * EQD_HEADS + OT_WLD) * 4 + (size_t)EQD_HEADS * OT_WLD * 2 + (size_t)cap * EQD_HEADS + 256;
   const size_t cbytes = (size_t)cap * EQD_HEADS * 8, fbytes = (size_t)cap * EQD_HEADS * 2;
   const size_t lim = 227 * 1024 - 2048;      // static shared memory of the kernel is ~1.5 KB
   OtLayout L;
@@ -118,22 +120,24 @@ __device__ inline OtView ot_carve(unsigned char* base, int cap, const OtLayout& 
   s.P = d; d += cap * 6;
   s.Y = d; d += EQD_HEADS * 6;
   s.u = d; d += cap;
-  s.ds = d; d += cap;
   s.v = d; d += EQD_HEADS;
   s.base_v = d; d += EQD_HEADS;
+  s.Wv = d; d += EQD_HEADS * OT_WLD;
+  s.dsink = d; d += OT_WLD;
   if (L.c_smem) { s.Cm = d; d += (size_t)cap * EQD_HEADS; } else s.Cm = c_global;
   int* i = reinterpret_cast<int*>(d);
   s.excess = i; i += cap;
-  s.par_s = i; i += cap;
   s.exl = i; i += cap;
   s.exq = i; i += cap;
   s.stamp = i; i += cap;
-  s.vislist = i; i += cap;
   s.deficit = i; i += EQD_HEADS;
   s.par_k = i; i += EQD_HEADS;
+  s.par_via = i; i += EQD_HEADS;
   s.fl_cnt = i; i += EQD_HEADS;
   s.base_i = i; i += EQD_HEADS;
+  s.ord = i; i += OT_WLD;
   short* h = reinterpret_cast<short*>(i);
+  s.Wi = h; h += EQD_HEADS * OT_WLD;
   if (L.fl_smem) { s.fls = h; h += (size_t)cap * EQD_HEADS; } else s.fls = fl_global;
   s.xs = reinterpret_cast<signed char*>(h);
   return s;
@@ -152,17 +156,22 @@ __device__ __forceinline__ void warp_argmin(double& v, int& k) {
 }
 
 // One CTA per pair: successive shortest augmenting paths with node potentials on the transport problem scaled to integers
-// (supply 50 per pocket point, demand n per keypoint, n * 50 units in all); the whole primal-dual loop runs in warp 0.
+// (supply 50 per pocket point, demand n per keypoint, n * 50 units in all).
 //   * Forward arcs form a complete bipartite graph and backward arcs (k -> i, x_ik > 0) have reduced cost 0 (complementary
-//     slackness), so Dijkstra only SETTLES SINKS: lane l owns sinks l and l + 32 (distances and parents in registers).
-//     All unsettled sinks at the current minimum distance are settled in one round (they are final: arc lengths >= 0;
-//     with potentials most of the search happens at distance 0); settling sink k reaches the sources feeding it (per-sink
-//     lists maintained by the augmenting lane), which relax the other sinks through the cached cost matrix.
+//     slackness), so the search only has to SETTLE SINKS; it runs on the sink graph (50 nodes): a settled sink k reaches the
+//     sources that feed it for free, hence every sink k' at  W[k][k'] - v[k'],  W[k][k'] = min over the feeders i of k of
+//     (C[i][k'] - u[i]).  Every augmentation starts with all four warps rebuilding W (50 x 50 minima over the ~n + 50
+//     non-zero flows, independent loads); the Dijkstra itself then runs in warp 0 out of registers -- lane l owns sinks l
+//     and l + 32 -- with one shared-memory row read per settled sink.  All unsettled sinks at the current minimum distance
+//     are settled in one round (arc lengths >= 0; with potentials most of the search happens at distance 0).
 //   * Potentials are kept modulo the common shift of an augmentation (u += D everywhere, v -= D everywhere leaves every
-//     reduced cost unchanged): only visited sources (u += D - ds) and settled sinks (v -= D - dk) are touched; the sources
-//     that still have excess all sit at distance 0 and share ONE lazy offset, so their contribution to the initial sink
-//     distances, base[k] = min_i (C_ik - u_i), changes only when the minimiser leaves the excess set.
+//     reduced cost unchanged): only the sources feeding settled sinks (u += D - d_sink, first sink in settle order) and the
+//     settled sinks (v -= D - d) are touched; the sources that still have excess all sit at distance 0 and share ONE lazy
+//     offset, so their contribution to the initial sink distances, base[k] = min_i (C_ik - u_i), changes only when the
+//     minimiser leaves the excess set.
 //   * All minima are lexicographic in (value, index): the plan does not depend on list or lane order.
+// (Round 2 first shipped the same algorithm with the sources expanded one by one inside warp 0: 39.5 ms for the `train` bench
+// batch, ~55 k cycles per augmentation in dependent shared-memory loads; see profiles/r02_ot_emd_*.)
 // The final flows are written to flow[(p0 + i) * 50 + k] (int32, global).
 __global__ void __launch_bounds__(LOSS_THREADS)
 ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const float* __restrict__ pocket_lig,
@@ -219,7 +228,6 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
     s.exl[i] = i;
     s.exq[i] = i;
     s.stamp[i] = 0;
-    s.par_s[i] = -1;
   }
   if (tid < M) { s.v[tid] = 0.0; s.deficit[tid] = n; s.fl_cnt[tid] = 0; }
   __syncthreads();
@@ -245,190 +253,217 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
     __syncthreads();
   }
   long n_aug = 0, n_pop = 0;
-  if (tid < 32) {
-    const int lane = tid;
-    const int k0 = lane, k1 = lane + 32;               // the two sinks this lane owns (k1 valid iff < M)
+  __shared__ int sh_mass, sh_fail;
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int k0 = lane, k1 = lane + 32;               // the two sinks a lane owns (k1 valid iff < M)
     const bool has1 = k1 < M;
-    int mass = n * M, nex = n, epoch = 0, fail = 0;
+    int mass = n * M, nex = n, epoch = 0, fail = 0;    // solver state: warp 0
     double u_ex_off = 0.0;
     const long max_aug = 64L * (n + M) + 1024;
     auto X = [&](int i, int k) -> int { return (int)s.xs[i * M + k]; };
-    while (mass > 0 && n_aug < max_aug) {
+    if (tid == 0) { sh_mass = mass; sh_fail = 0; }
+    __syncthreads();
+    while (sh_mass > 0 && !sh_fail && n_aug < max_aug) {
       ++n_aug;
       ++epoch;
-      // (+ 0.0 turns a -0.0 into +0.0: warp_argmin orders distances by their bit patterns)
-      double d0 = fmax(s.base_v[k0] - u_ex_off - s.v[k0], 0.0) + 0.0, d1 = has1 ? fmax(s.base_v[k1] - u_ex_off - s.v[k1], 0.0) + 0.0 : INFINITY;
-      int p0_ = s.base_i[k0], p1_ = has1 ? s.base_i[k1] : -1;
-      const double v0 = s.v[k0], v1 = has1 ? s.v[k1] : 0.0;
-      bool set0 = false, set1 = !has1;
-      int nvis = 0, target = -1;
-      double D = 0.0;
-      for (int round = 0; round <= M; ++round) {
-        double bv = INFINITY;
-        int bk = 0x7fffffff;
-        if (!set0) { bv = d0; bk = k0; }
-        if (!set1 && (d1 < bv || (d1 == bv && k1 < bk))) { bv = d1; bk = k1; }
-        warp_argmin(bv, bk);
-        ++n_pop;
-        if (bk >= M || !(bv < INFINITY)) break;
-        // every unsettled sink at distance bv is final; a deficit among them ends the search (lowest index wins)
-        const bool at0 = !set0 && d0 == bv, at1 = !set1 && d1 == bv;
-        const unsigned m0 = __ballot_sync(0xffffffffu, at0), m1 = __ballot_sync(0xffffffffu, at1);
-        const unsigned t0 = __ballot_sync(0xffffffffu, at0 && s.deficit[k0] > 0);
-        const unsigned t1 = __ballot_sync(0xffffffffu, at1 && s.deficit[has1 ? k1 : 0] > 0);
-        if (t0 | t1) { target = t0 ? (__ffs(t0) - 1) : (32 + __ffs(t1) - 1); D = bv; break; }
-        if (at0) set0 = true;
-        if (at1) set1 = true;
-        const int first_new = nvis;
-        // settle them in ascending sink order: the sources feeding a sink become reachable at distance bv
-        for (int half = 0; half < 2; ++half) {
-          unsigned mm = half == 0 ? m0 : m1;
-          while (mm) {
-            const int bit = __ffs(mm) - 1;
-            mm &= mm - 1;
-            const int ks = half * 32 + bit;
+      // ---- A (all warps): the sink graph.  A settled sink k reaches, at no cost, the sources that feed it (backward arcs of
+      // reduced cost 0), and through source i every sink k' at C[i][k'] - u[i] - v[k']: its outgoing arc lengths are
+      // W[k][k'] - v[k'] with W[k][k'] = min over the feeders of k of (C[i][k'] - u[i]).  Sources that still have excess are
+      // skipped: they sit at distance 0 and act through base[] (their potential carries the lazy offset).
+      for (int k = warp; k < M; k += LOSS_THREADS / 32) {
+        const int cnt = s.fl_cnt[k];
+        double w0 = INFINITY, w1 = INFINITY;
+        int i0 = 0x7fffffff, i1 = 0x7fffffff;
+        for (int q = 0; q < cnt; q += 4) {
+          int ii[4], ex[4];
+          double ui[4], c0[4], c1[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) ii[t] = (int)s.fls[k * n + min(q + t, cnt - 1)];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            ex[t] = s.excess[ii[t]];
+            ui[t] = s.u[ii[t]];
+            c0[t] = s.Cm[ii[t] * M + k0];
+            c1[t] = has1 ? s.Cm[ii[t] * M + k1] : INFINITY;
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (q + t < cnt && ex[t] == 0) {
+              const double a0 = c0[t] - ui[t], a1 = c1[t] - ui[t];
+              if (a0 < w0 || (a0 == w0 && ii[t] < i0)) { w0 = a0; i0 = ii[t]; }
+              if (a1 < w1 || (a1 == w1 && ii[t] < i1)) { w1 = a1; i1 = ii[t]; }
+            }
+          }
+        }
+        s.Wv[k * OT_WLD + k0] = w0;
+        s.Wv[k * OT_WLD + k1] = w1;
+        s.Wi[k * OT_WLD + k0] = (short)(i0 == 0x7fffffff ? -1 : i0);
+        s.Wi[k * OT_WLD + k1] = (short)(i1 == 0x7fffffff || !has1 ? -1 : i1);
+      }
+      __syncthreads();
+      if (tid < 32) {
+        // ---- B: Dijkstra over the sinks (lane l owns sinks l and l + 32: distances and parents in registers).  All unsettled
+        // sinks at the current minimum distance are settled in one round (arc lengths >= 0); a deficit among them ends the search.
+        // (+ 0.0 turns a -0.0 into +0.0: warp_argmin orders distances by their bit patterns)
+        double d0 = fmax(s.base_v[k0] - u_ex_off - s.v[k0], 0.0) + 0.0, d1 = has1 ? fmax(s.base_v[k1] - u_ex_off - s.v[k1], 0.0) + 0.0 : INFINITY;
+        int p0_ = s.base_i[k0], p1_ = has1 ? s.base_i[k1] : -1;     // parent source ...
+        int via0 = -1, via1 = -1;                                   // ... and the sink it was reached through (-1: it has excess)
+        const double v0 = s.v[k0], v1 = has1 ? s.v[k1] : 0.0;
+        bool set0 = false, set1 = !has1;
+        int target = -1, nord = 0;
+        double D = 0.0;
+        for (int round = 0; round <= M; ++round) {
+          double bv = INFINITY;
+          int bk = 0x7fffffff;
+          if (!set0) { bv = d0; bk = k0; }
+          if (!set1 && (d1 < bv || (d1 == bv && k1 < bk))) { bv = d1; bk = k1; }
+          warp_argmin(bv, bk);
+          ++n_pop;
+          if (bk >= M || !(bv < INFINITY)) break;
+          const bool at0 = !set0 && d0 == bv, at1 = !set1 && d1 == bv;
+          const unsigned m0 = __ballot_sync(0xffffffffu, at0), m1 = __ballot_sync(0xffffffffu, at1);
+          const unsigned t0 = __ballot_sync(0xffffffffu, at0 && s.deficit[k0] > 0);
+          const unsigned t1 = __ballot_sync(0xffffffffu, at1 && s.deficit[has1 ? k1 : 0] > 0);
+          if (t0 | t1) { target = t0 ? (__ffs(t0) - 1) : (32 + __ffs(t1) - 1); D = bv; break; }
+          if (at0) set0 = true;
+          if (at1) set1 = true;
+          // relax my unsettled sinks from the newly settled ones, in ascending sink order (minima are lexicographic in
+          // (distance, parent source): the plan does not depend on lane order)
+          for (int hf = 0; hf < 2; ++hf) {
+            unsigned mm = hf == 0 ? m0 : m1;
+            while (mm) {
+              const int bit = __ffs(mm) - 1;
+              mm &= mm - 1;
+              const int ks = hf * 32 + bit;
+              if (lane == 0) { s.ord[nord] = ks; s.dsink[nord] = bv; }
+              ++nord;
+              const int s0 = (int)s.Wi[ks * OT_WLD + k0], s1 = (int)s.Wi[ks * OT_WLD + k1];
+              if (!set0 && s0 >= 0) {
+                const double nd0 = fmax(s.Wv[ks * OT_WLD + k0] - v0, 0.0) + bv;
+                if (nd0 < d0 || (nd0 == d0 && s0 < p0_)) { d0 = nd0; p0_ = s0; via0 = ks; }
+              }
+              if (!set1 && s1 >= 0) {
+                const double nd1 = fmax(s.Wv[ks * OT_WLD + k1] - v1, 0.0) + bv;
+                if (nd1 < d1 || (nd1 == d1 && s1 < p1_)) { d1 = nd1; p1_ = s1; via1 = ks; }
+              }
+            }
+          }
+        }
+        if (target < 0) fail |= 2;
+        int left = -1;                                   // a source that just lost its last unit of excess
+        if (!fail) {
+          if (set0 || k0 == target) { s.par_k[k0] = p0_; s.par_via[k0] = via0; }
+          if (has1 && (set1 || k1 == target)) { s.par_k[k1] = p1_; s.par_via[k1] = via1; }
+          // ---- C: potentials (kept modulo the common shift of an augmentation: u += D everywhere, v -= D everywhere leaves every
+          // reduced cost unchanged).  Settled sinks: v -= D - d; a source without excess that feeds a settled sink was reached at
+          // that sink's distance (the first one in settle order): u += D - d; the sources with excess share the lazy offset.
+          if (set0) s.v[k0] = v0 - (D - d0);
+          if (has1 && set1) s.v[k1] = v1 - (D - d1);
+          __syncwarp();
+          for (int o = 0; o < nord; ++o) {
+            const int ks = s.ord[o];
+            const double du = D - s.dsink[o];
             const int cnt = s.fl_cnt[ks];
-            for (int q0 = 0; q0 < cnt; q0 += 32) {
-              const int q = q0 + lane;
-              int i = -1;
-              bool ok = false;
-              if (q < cnt) {
-                i = (int)s.fls[ks * n + q];
-                ok = s.excess[i] == 0 && s.stamp[i] != epoch;
-              }
-              const unsigned mk = __ballot_sync(0xffffffffu, ok);
-              if (ok) {
+            for (int q = lane; q < cnt; q += 32) {
+              const int i = (int)s.fls[ks * n + q];
+              if (s.excess[i] == 0 && s.stamp[i] != epoch) {
                 s.stamp[i] = epoch;
-                s.ds[i] = bv;
-                s.par_s[i] = ks;
-                s.vislist[nvis + __popc(mk & ((1u << lane) - 1u))] = i;
-              }
-              nvis += __popc(mk);
-              __syncwarp();
-            }
-          }
-        }
-        // relax my unsettled sinks through the newly reached sources; 8 sources per step so that the dependent
-        // shared-memory loads (list -> potential, cost row) of different sources overlap
-        if (!set0 || !set1) {
-          for (int q = first_new; q < nvis; q += 8) {
-            int ii[8];
-            double c0[8], c1[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) ii[t] = s.vislist[min(q + t, nvis - 1)];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const double ui = s.u[ii[t]];
-              c0[t] = s.Cm[ii[t] * M + k0] - ui;
-              c1[t] = has1 ? s.Cm[ii[t] * M + k1] - ui : 0.0;
-            }
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              if (q + t < nvis) {
-                const double nd0 = fmax(c0[t] - v0, 0.0) + bv, nd1 = fmax(c1[t] - v1, 0.0) + bv;
-                if (!set0 && (nd0 < d0 || (nd0 == d0 && ii[t] < p0_))) { d0 = nd0; p0_ = ii[t]; }
-                if (!set1 && (nd1 < d1 || (nd1 == d1 && ii[t] < p1_))) { d1 = nd1; p1_ = ii[t]; }
+                s.u[i] += du;
               }
             }
+            __syncwarp();
+          }
+          u_ex_off += D;
+          // ---- D: augment along the parent chain and maintain the lists (lane 0) ----
+          if (lane == 0) {
+            int delta = s.deficit[target];
+            int k = target, i = s.par_k[k], hops = 0;
+            while (s.excess[i] == 0) {                     // reached through a backward arc of sink par_via[k]
+              const int pk = s.par_via[k];
+              if (pk < 0 || ++hops > 2 * M + 2) { fail |= 4; delta = 0; break; }
+              delta = min(delta, X(i, pk));
+              k = pk;
+              i = s.par_k[k];
+            }
+            delta = min(delta, s.excess[i]);
+            if (delta > 0) {
+              k = target;
+              i = s.par_k[k];
+              s.deficit[target] -= delta;
+              while (true) {
+                const int xf = X(i, k);
+                if (xf == 0) s.fls[k * n + s.fl_cnt[k]++] = (short)i;      // i starts feeding k
+                s.xs[i * M + k] = (signed char)(xf + delta);
+                if (s.excess[i] > 0) {
+                  s.excess[i] -= delta;
+                  if (s.excess[i] == 0) left = i;
+                  break;
+                }
+                const int pk = s.par_via[k];
+                const int xb = X(i, pk) - delta;
+                s.xs[i * M + pk] = (signed char)xb;
+                if (xb == 0) {                             // i stops feeding pk: swap-remove it from pk's list
+                  const int c = --s.fl_cnt[pk];
+                  int q = 0;
+                  while (q < c && (int)s.fls[pk * n + q] != i) ++q;
+                  s.fls[pk * n + q] = s.fls[pk * n + c];
+                }
+                k = pk;
+                i = s.par_k[k];
+              }
+              mass -= delta;
+            } else {
+              fail |= 8;
+              mass = 0;
+            }
+          }
+          mass = __shfl_sync(0xffffffffu, mass, 0);
+          left = __shfl_sync(0xffffffffu, left, 0);
+          fail = __shfl_sync(0xffffffffu, fail, 0);
+        }
+        if (!fail && left >= 0) {
+          // the source leaves the excess set: materialise its potential, drop it from the list, and recompute the base of
+          // the sinks whose minimiser it was (base[k] = min over the sources with excess of C_ik - u_i)
+          if (lane == 0) {
+            s.u[left] += u_ex_off;
+            const int q = s.exq[left], last = s.exl[nex - 1];
+            s.exl[q] = last;
+            s.exq[last] = q;
+          }
+          nex -= 1;
+          __syncwarp();
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int k = t == 0 ? k0 : k1;
+            if (k < M && s.base_i[k] == left) {
+              double best = INFINITY;
+              int bi = 0x7fffffff;
+              for (int q = 0; q < nex; q += 4) {
+                int ii[4];
+                double cc[4];
+#pragma unroll
+                for (int t2 = 0; t2 < 4; ++t2) ii[t2] = s.exl[min(q + t2, nex - 1)];
+#pragma unroll
+                for (int t2 = 0; t2 < 4; ++t2) cc[t2] = s.Cm[ii[t2] * M + k] - s.u[ii[t2]];
+#pragma unroll
+                for (int t2 = 0; t2 < 4; ++t2)
+                  if (q + t2 < nex && (cc[t2] < best || (cc[t2] == best && ii[t2] < bi))) { best = cc[t2]; bi = ii[t2]; }
+              }
+              s.base_v[k] = best;
+              s.base_i[k] = bi;
+            }
           }
         }
+        if (lane == 0) { sh_mass = mass; sh_fail = fail; }
       }
-      if (target < 0) { fail |= 2; break; }
-      if (set0 || k0 == target) s.par_k[k0] = p0_;
-      if (has1 && (set1 || k1 == target)) s.par_k[k1] = p1_;
-      if (set0) s.v[k0] = v0 - (D - d0);
-      if (has1 && set1) s.v[k1] = v1 - (D - d1);
-      for (int q = lane; q < nvis; q += 32) {
-        const int i = s.vislist[q];
-        s.u[i] += D - s.ds[i];
-      }
-      u_ex_off += D;
-      __syncwarp();
-      // ---- augment along the parent chain and maintain the lists (lane 0) ----
-      int left = -1;                                   // a source that just lost its last unit of excess
-      if (lane == 0) {
-        int delta = s.deficit[target];
-        int k = target, i = s.par_k[k], hops = 0;
-        while (s.excess[i] == 0) {                     // reached through a backward arc
-          const int pk = s.par_s[i];
-          delta = min(delta, X(i, pk));
-          k = pk;
-          i = s.par_k[k];
-          if (++hops > 2 * M + 2) { fail |= 4; delta = 0; break; }
-        }
-        delta = min(delta, s.excess[i]);
-        if (delta > 0) {
-          k = target;
-          i = s.par_k[k];
-          s.deficit[target] -= delta;
-          while (true) {
-            const int xf = X(i, k);
-            if (xf == 0) s.fls[k * n + s.fl_cnt[k]++] = (short)i;      // i starts feeding k
-            s.xs[i * M + k] = (signed char)(xf + delta);
-            if (s.excess[i] > 0) {
-              s.excess[i] -= delta;
-              if (s.excess[i] == 0) left = i;
-              break;
-            }
-            const int pk = s.par_s[i];
-            const int xb = X(i, pk) - delta;
-            s.xs[i * M + pk] = (signed char)xb;
-            if (xb == 0) {                             // i stops feeding pk: swap-remove it from pk's list
-              const int c = --s.fl_cnt[pk];
-              int q = 0;
-              while (q < c && (int)s.fls[pk * n + q] != i) ++q;
-              s.fls[pk * n + q] = s.fls[pk * n + c];
-            }
-            k = pk;
-            i = s.par_k[k];
-          }
-          mass -= delta;
-        } else {
-          fail |= 8;
-          mass = 0;
-        }
-      }
-      mass = __shfl_sync(0xffffffffu, mass, 0);
-      left = __shfl_sync(0xffffffffu, left, 0);
-      fail = __shfl_sync(0xffffffffu, fail, 0);
-      if (fail) break;
-      if (left >= 0) {
-        // the source leaves the excess set: materialise its potential, drop it from the list, and recompute the base of
-        // the sinks whose minimiser it was
-        if (lane == 0) {
-          s.u[left] += u_ex_off;
-          const int q = s.exq[left], last = s.exl[nex - 1];
-          s.exl[q] = last;
-          s.exq[last] = q;
-        }
-        nex -= 1;
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int k = t == 0 ? k0 : k1;
-          if (k < M && s.base_i[k] == left) {
-            double best = INFINITY;
-            int bi = 0x7fffffff;
-            for (int q = 0; q < nex; q += 4) {
-              int ii[4];
-              double cc[4];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) ii[t] = s.exl[min(q + t, nex - 1)];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) cc[t] = s.Cm[ii[t] * M + k] - s.u[ii[t]];
-#pragma unroll
-              for (int t = 0; t < 4; ++t)
-                if (q + t < nex && (cc[t] < best || (cc[t] == best && ii[t] < bi))) { best = cc[t]; bi = ii[t]; }
-            }
-            s.base_v[k] = best;
-            s.base_i[k] = bi;
-          }
-        }
-      }
-      __syncwarp();
+      __syncthreads();
     }
-    if (mass > 0) fail |= 16;
-    if (lane == 0 && fail) atomicOr(err, fail);
+    if (tid == 0) {
+      int fail = sh_fail;
+      if (sh_mass > 0) fail |= 16;
+      if (fail) atomicOr(err, fail);
+    }
   }
   __syncthreads();
   // ---- value and keypoint gradients from the (constant) plan T = x / (n * M) ----

@@ -505,4 +505,4 @@ class DataParallelTrainer:
                                              self.layout.total, nat.ptr(self.sq), 256, h['clip'], h['lr'], h['b1'], h['b2'], h['eps'],
                                              h['wd'], self.steps, 1.0 / self.world, nat.ptr(self.norm), st), 'eqd_clip_adam')
             self.invalidate_packed()
-        return {'loss': res['total'], 'grad_norm': self.norm, 'err': res['err'], 'fwd': fwd}
+        return {'loss': res['total'], 'grad_norm': self.norm, 'err': res['err'], 'fwd': fwd, 'parts': res['parts']}
