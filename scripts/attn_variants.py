@@ -15,7 +15,7 @@ plan = GraphPlan.from_graph(g, dev, 10)
 N = plan.N
 torch.manual_seed(0)
 proj = torch.randn(N, 320, device=dev) * 0.5
-kv = torch.empty(main.eqd_kv_blocks_bytes(N), dtype=torch.uint8, device=dev)
+kv = torch.zeros(main.eqd_kv_blocks_bytes(N), dtype=torch.uint8, device=dev)
 nat.check(main.eqd_kv_blocks(C.byref(plan.struct), nat.ptr(proj), 320, 192, 256, nat.ptr(kv), None), 'kv_blocks')
 torch.cuda.synchronize()
 stream = torch.cuda.current_stream().cuda_stream
