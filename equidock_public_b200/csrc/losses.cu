@@ -296,8 +296,9 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
             }
           }
         }
-        s.Wv[k * OT_WLD + k0] = w0;
-        s.Wv[k * OT_WLD + k1] = w1;
+        // stored as arc lengths k -> k': W - v[k'] clamped at 0 (reduced costs are >= 0 up to rounding)
+        s.Wv[k * OT_WLD + k0] = fmax(w0 - s.v[k0], 0.0);
+        s.Wv[k * OT_WLD + k1] = has1 ? fmax(w1 - s.v[k1], 0.0) : INFINITY;
         s.Wi[k * OT_WLD + k0] = (short)(i0 == 0x7fffffff ? -1 : i0);
         s.Wi[k * OT_WLD + k1] = (short)(i1 == 0x7fffffff || !has1 ? -1 : i1);
       }
@@ -310,6 +311,7 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
         int p0_ = s.base_i[k0], p1_ = has1 ? s.base_i[k1] : -1;     // parent source ...
         int via0 = -1, via1 = -1;                                   // ... and the sink it was reached through (-1: it has excess)
         const double v0 = s.v[k0], v1 = has1 ? s.v[k1] : 0.0;
+        const bool def0 = s.deficit[k0] > 0, def1 = has1 && s.deficit[k1] > 0;   // deficits do not change during a search
         bool set0 = false, set1 = !has1;
         int target = -1, nord = 0;
         double D = 0.0;
@@ -323,8 +325,8 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
           if (bk >= M || !(bv < INFINITY)) break;
           const bool at0 = !set0 && d0 == bv, at1 = !set1 && d1 == bv;
           const unsigned m0 = __ballot_sync(0xffffffffu, at0), m1 = __ballot_sync(0xffffffffu, at1);
-          const unsigned t0 = __ballot_sync(0xffffffffu, at0 && s.deficit[k0] > 0);
-          const unsigned t1 = __ballot_sync(0xffffffffu, at1 && s.deficit[has1 ? k1 : 0] > 0);
+          const unsigned t0 = __ballot_sync(0xffffffffu, at0 && def0);
+          const unsigned t1 = __ballot_sync(0xffffffffu, at1 && def1);
           if (t0 | t1) { target = t0 ? (__ffs(t0) - 1) : (32 + __ffs(t1) - 1); D = bv; break; }
           if (at0) set0 = true;
           if (at1) set1 = true;
@@ -340,11 +342,11 @@ ot_emd_kernel(int n_pairs, int cap, const int* __restrict__ pocket_ptr, const fl
               ++nord;
               const int s0 = (int)s.Wi[ks * OT_WLD + k0], s1 = (int)s.Wi[ks * OT_WLD + k1];
               if (!set0 && s0 >= 0) {
-                const double nd0 = fmax(s.Wv[ks * OT_WLD + k0] - v0, 0.0) + bv;
+                const double nd0 = s.Wv[ks * OT_WLD + k0] + bv;
                 if (nd0 < d0 || (nd0 == d0 && s0 < p0_)) { d0 = nd0; p0_ = s0; via0 = ks; }
               }
               if (!set1 && s1 >= 0) {
-                const double nd1 = fmax(s.Wv[ks * OT_WLD + k1] - v1, 0.0) + bv;
+                const double nd1 = s.Wv[ks * OT_WLD + k1] + bv;
                 if (nd1 < d1 || (nd1 == d1 && s1 < p1_)) { d1 = nd1; p1_ = s1; via1 = ks; }
               }
             }
