@@ -15,6 +15,10 @@
 //     -> msg (+bias) -> fp32 tile in smem (mean aggregation at the destination nodes)
 //     -> coordinate MLP hidden layer -> LeakyReLU, dot w4 -> phi ; x' = eta x0 + (1-eta) x + mean(x_rel phi) in fp64.
 // Per-edge activations never leave the SM; weights are read from HBM/L2 once per CTA.
+// The kernel is bound by the dependent chain of a tile group, not by a pipe (profiles/r02_edge_variants.txt): the serial tail of
+// a tile is kept short (a tile whose nodes all have 10 in-edges -- a k-NN graph -- needs no row_ptr lookups; the next tile's
+// coordinate gathers leave two GEMMs early; the coordinate update runs on threads that do no aggregation) and the fp32
+// epilogue arithmetic is written on lane pairs (add / mul / fma.f32x2: the same IEEE results in half the instructions).
 #include "tc_common.cuh"
 
 namespace eqd {
@@ -104,7 +108,7 @@ edge_stage_tc_kernel(eqd_graph g, eqd_layer_params p, const __grid_constant__ Ed
   unsigned mma_phase = 0, mma2_phase = 0, he_phase = 0, a_phase = 0;
   const unsigned w_saddr = smem_u32(S.w);
 
-  // Prefetch of a tile's indices + he rows (issued by the half-0 threads).
+  // Prefetch of a tile's indices, Pdst rows and he rows.
   auto prefetch = [&](int tile, int buf, int& e0_out, int& ne_out, int& off_l, int& n_l, int& off_r) {
     const int n0 = tile * tn, nn = min(tn, g.n_nodes - n0);
     const int e0 = __ldg(g.row_ptr + n0), e1 = __ldg(g.row_ptr + n0 + nn);
