@@ -90,7 +90,7 @@ loss_mse_intersection_kernel(eqd_graph g, const float* __restrict__ pred, const 
 
 // Per-CTA state of the transport solver, carved from dynamic shared memory for a pocket capacity `cap` (the largest pocket
 // of the batch).  The cost matrix C (fp64, cap x 50) and the per-sink source lists (int16) live in shared memory when they
-// fit (cap <= 346: both; <= 410: C only; <= 917: lists only), else in global memory (L2); flows x_ik <= 50 are int8.
+// fit (cap <= 310: both; <= 370: C only; <= 870: lists only), else in global memory (L2); flows x_ik <= 50 are int8.
 struct OtView {
   double *P, *Y, *u, *v, *base_v, *Cm;
   double *Wv, *dsink;          // sink graph: Wv[k][64] = min over the feeders i of sink k of C[i][.] - u[i]; settle distances
