@@ -128,7 +128,7 @@ def edge_stage_algorithmic_flops(n_edges: int, dh: int = 64) -> float:
 EDGE_TC_BF16_FLOP_PER_EDGE = 2.0 * (48 * 64 + 64 * 128) * 6
 # dram__bytes_read.sum + dram__bytes_write.sum of one edge_stage_tc_kernel launch of the headline workload
 # (ncu --set full, profiles/): filled from the committed summary of the current round
-EDGE_TC_NCU_TRAFFIC_BYTES = 195.6e6   # profiles/r02_edge_stage_tc_ncu_summary.txt: 176.5 MB read + 19.1 MB written
+EDGE_TC_NCU_TRAFFIC_BYTES = 195.3e6   # profiles/r02_final_edge_stage_tc_ncu_summary.txt: 176.5 MB read + 18.7 MB written
 
 
 def bind_to_gpu_numa(local_rank: int):
