@@ -7,7 +7,10 @@
 
 Workloads (BASELINE.json configs):
   db5-shaped   (headline, north_star / configs[1] shape) synthetic DB5.5-shaped residue graphs, 200+200 residues, k=10,
-               8-layer IEGMN with the shipped DIPS checkpoint's weights, batched inference, 256 pairs/step/GPU.
+               8-layer IEGMN with the shipped DIPS checkpoint's weights, batched inference, 370 pairs/step/GPU (the batch is
+               sized to the machine: 370 pairs = 1480 attention tiles, 1157 node tiles and 12 334 edge tiles, i.e. 5.00 / 3.91 /
+               41.7 rounds of the 296 resident tile groups of a B200, where 256 pairs left the last attention / node round
+               54 % / 30 % empty: +5.5 % pairs/s).
   db5-testset  (configs[1] literally) 25 pairs with the (N_l, N_r) sizes of the DB5.5 test set as ONE ragged batch.
   large        (configs[4]) synthetic 2000+2000-residue complexes, 8 pairs/step/GPU.
   train        (configs[2]/[3]) DIPS-shaped ragged batch of 32 pairs/GPU, 5-layer shared IEGMN, forward + losses
@@ -59,7 +62,7 @@ def db5_test_sizes():
 
 
 WORKLOADS = {
-    'db5-shaped': dict(n_layers=8, ckpt='dips', pairs_per_gpu=256, flop_per_pair=1.781e9, bytes_per_pair=6.20e6,
+    'db5-shaped': dict(n_layers=8, ckpt='dips', pairs_per_gpu=370, flop_per_pair=1.781e9, bytes_per_pair=6.20e6,
                        text='synthetic DB5.5-shaped 200+200 residues k=10, 8-layer IEGMN (DIPS checkpoint weights), '
                             'batched inference'),
     'db5-testset': dict(n_layers=8, ckpt='dips', pairs_per_gpu=25, flop_per_pair=None, bytes_per_pair=None,
@@ -128,7 +131,8 @@ def edge_stage_algorithmic_flops(n_edges: int, dh: int = 64) -> float:
 EDGE_TC_BF16_FLOP_PER_EDGE = 2.0 * (48 * 64 + 64 * 128) * 6
 # dram__bytes_read.sum + dram__bytes_write.sum of one edge_stage_tc_kernel launch of the headline workload
 # (ncu --set full, profiles/): filled from the committed summary of the current round
-EDGE_TC_NCU_TRAFFIC_BYTES = 195.3e6   # profiles/r02_final_edge_stage_tc_ncu_summary.txt: 176.5 MB read + 18.7 MB written
+EDGE_TC_NCU_TRAFFIC_BYTES = {370: 286.8e6,   # profiles/r02_final_edge_stage_tc_370pairs_ncu_summary.txt: 255.1 MB read + 31.7 MB written
+                             256: 195.3e6}   # profiles/r02_final_edge_stage_tc_ncu_summary.txt: 176.5 MB read + 18.7 MB written
 
 
 def bind_to_gpu_numa(local_rank: int):
@@ -599,7 +603,7 @@ def run_engine(args, rank, local_rank, world):
         'clocks': {**clocks, 'per_rank_sm_mhz': rank_clocks},
         'roofline': {'kernel': 'edge_stage_tc_kernel', 'bound': 'tensor', 'achieved': alg_flops / (edge_ms * 1e-3) / 1e12,
                      'peak': tc_peak, 'unit': 'TFLOP/s', 'frac': alg_flops / (edge_ms * 1e-3) / 1e12 / tc_peak,
-                     'traffic': EDGE_TC_NCU_TRAFFIC_BYTES if (args.workload == 'db5-shaped' and B == 256) else None,
+                     'traffic': EDGE_TC_NCU_TRAFFIC_BYTES.get(B) if args.workload == 'db5-shaped' else None,
                      'peak_source': peak_src + ', sustained bf16',
                      'algorithmic_flops_per_launch': alg_flops, 'launch_ms': edge_ms,
                      'launch_ms_source': f'CUDA events recorded by eqd_iegmn_forward around every edge-stage launch over an '
