@@ -340,11 +340,18 @@ def run_reference(args, rank, world):
         pairs, _, _ = bench_train.make_train_pairs(args, 0, world, sys.modules[__name__])
     else:
         pairs, _, _ = make_pairs(args, 0, world)
-    sample = len(pairs) if args.ref_sample <= 0 else min(args.ref_sample, len(pairs))
-    pairs = pairs[:sample]
     pool = ReferencePool(cores, args.workload)
     for _ in range(max(1, min(args.warmup, 2))):
         pool.run(pairs[:pool.workers])
+    if args.ref_sample > 0:
+        sample = min(args.ref_sample, len(pairs))
+    else:   # the whole step batch, unless K steps of it would not end within a few minutes on this box: then a bounded prefix
+        ncal = min(len(pairs), 2 * pool.workers)
+        tc = time.perf_counter()
+        pool.run(pairs[:ncal])
+        rate = ncal / max(time.perf_counter() - tc, 1e-6)
+        sample = min(len(pairs), max(pool.workers, int(rate * args.ref_budget_s / max(args.steps, 1))))
+    pairs = pairs[:sample]
     t0 = time.perf_counter()
     for _ in range(args.steps):
         pool.run(pairs)
@@ -664,6 +671,8 @@ def main():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--ref-sample', type=int, default=0,
                     help='pairs per step of the CPU reference arm (0 = the whole rank-0 step batch, like the engine arm)')
+    ap.add_argument('--ref-budget-s', type=float, default=240.0,
+                    help='CPU reference arm: shrink the per-step sample so that the K timed steps fit in about this many seconds')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-cuda-graph', action='store_true')
