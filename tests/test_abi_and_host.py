@@ -255,3 +255,20 @@ def test_tensor_core_panels_decode_to_the_reference_weights(ds, li):
         assert float(w5d[69:].abs().max()) == 0.0 and float(w5d[:, 69:80].abs().max()) == 0.0
         w6d = _umma_decode(nd[3 * 80 * 224:], 64, 80)
         assert close(w6d[:, :69], w6) and float(w6d[:, 69:].abs().max()) == 0.0
+
+
+def test_default_bench_batch_fills_whole_rounds_of_tile_groups():
+    """bench.py's headline batch (370 pairs of 200 + 200 residues per GPU) is sized to the machine: the tile kernels are persistent
+    with 2 tile groups on each of the 148 SMs, and 370 pairs give (nearly) whole rounds of attention / node / edge tiles where
+    256 pairs left the last attention and node rounds half empty."""
+    import math
+    import bench
+    B = bench.WORKLOADS['db5-shaped']['pairs_per_gpu']
+    groups = 148 * 2
+    def eff(b):
+        tiles = {'attention': 2 * b * math.ceil(200 / nat.TILE_ROWS), 'node': math.ceil(400 * b / nat.TILE_ROWS),
+                 'edge': math.ceil(400 * b / (nat.TILE_ROWS // 10))}
+        return {k: (t / groups) / math.ceil(t / groups) for k, t in tiles.items()}
+    e = eff(B)
+    assert B == 370 and min(e.values()) > 0.97, e
+    assert eff(256)['attention'] < 0.87 and eff(256)['node'] < 0.91
